@@ -1,0 +1,127 @@
+/* bayes_portfolio.h — C ABI of libbayes_portfolio.so (sm_100a).
+ *
+ * Drop-in boundary for ONE hot path of vilnik/incorporating-different-sources: the rolling-window
+ * Bayesian tangency-portfolio weight computation of src/portfolio_calculations.py as driven by the
+ * backtest loop.  The reference has no FFI of its own (pure Python); these entry
+ * points are what a ctypes binding of that path binds — see INTEGRATION.md for the stub — and each
+ * cites the reference interface it replaces (file:line into /root/reference/src/).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / pandas types cross this boundary;
+ *  - every function returns 0 on success, non-zero on error; bp_last_error() has the message
+ *    (the Python shim maps the codes onto the reference's exception types);
+ *  - the market (prices, caps, MCM series, risk-free rate) is uploaded once and stays resident in
+ *    HBM; window batches are described by integer row indices computed on the host;
+ *  - OUTPUT pointers may be host pointers (pageable or pinned) or device pointers; the library
+ *    detects which.  With host outputs the call returns after the data has landed; with device
+ *    outputs it is asynchronous on the handle's stream;
+ *  - all floating point is IEEE double; all indices are int32 row numbers into the uploaded arrays.
+ */
+#ifndef BAYES_PORTFOLIO_H
+#define BAYES_PORTFOLIO_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BP_OK 0
+#define BP_ERR_INVALID 1      /* bad argument (maps to ValueError)                                  */
+#define BP_ERR_CUDA 2         /* CUDA runtime / driver failure (RuntimeError)                        */
+#define BP_ERR_NO_DEVICE 3    /* no usable sm_100 device: the library never falls back to the CPU    */
+#define BP_ERR_STATE 4        /* call order violated, e.g. no market uploaded                        */
+
+#define BP_NSCAL 12           /* doubles per window in bp_outputs.scalars                            */
+/* indices into the per-window scalar record */
+#define BP_SCAL_N0 0          /* conjugate prior n0            portfolio_calculations.py:247-267     */
+#define BP_SCAL_N1 1          /* posterior n1 = n0 + n         :269-282                              */
+#define BP_SCAL_ALPHA 2       /* n0 * m/(m-1)                  :317-318,:333                         */
+#define BP_SCAL_BETA 3        /* rank-1 coefficient used by the Gram epilogue                       */
+#define BP_SCAL_C 4           /* conjugate c                   :382-430                              */
+#define BP_SCAL_V0 5          /* w0' S0 w0                     :64-88                                */
+#define BP_SCAL_M 6           /* number of HF returns m        :314                                  */
+#define BP_SCAL_SUMA 7        /* sum of risk-free adjustments  :48                                   */
+#define BP_SCAL_V1 8          /* w1' S1 w1                     :574                                  */
+
+typedef struct bp_handle bp_handle;
+
+/* The data the weight functions read (the frames of data_handling.py:282-291, already aligned to
+ * one business-day calendar by the host).  Row-major, densely packed (leading dimension n_assets). */
+typedef struct {
+    int n_assets;               /* N: columns of every matrix, in the caller's column order          */
+    int n_days;                 /* D: rows of prices / caps / mcm / rf_row                           */
+    long long n_hf_rows;        /* R: rows of hf_prices (may be 0 for Jeffreys-only use)             */
+    const double* prices;       /* [D][N] daily close           -> k_stock_prices_df                 */
+    const double* caps;         /* [D][N] market caps           -> k_stock_market_caps_df (may be NULL) */
+    const double* hf_prices;    /* [R][N] intraday prices       -> k_stock_intraday_prices_df        */
+    const double* mcm;          /* [n_mcm][D] VIX / EPU ...     -> mcm_prices_df (may be NULL)       */
+    int n_mcm;
+    const double* rf_row;       /* [D] annualised risk-free rate forward-filled onto the daily rows
+                                   (risk_free_rate_df.reindex(method='ffill'), :54)                  */
+} bp_market_desc;
+
+/* One batch of rebalance windows sharing a portfolio_spec (portfolio_specs.py:80-90). */
+typedef struct {
+    int n_windows;              /* W                                                                 */
+    int rolling_window;         /* spec["rolling_window"]: n prices -> n-1 returns (:159, F2)        */
+    const int* day_row;         /* [W] row of trading_date_ts in the daily arrays (:145)             */
+    const int* span_days;       /* [W] calendar days between first and last window date (:40-41)     */
+    const int* hf_lo;           /* [W] first intraday PRICE row with ts > d - D + 1 day (:310-312)   */
+    const int* hf_hi;           /* [W] one past the last intraday row with ts <= d + 1 day           */
+    int mcm_index;              /* which uploaded MCM series (VIX / EPU)                             */
+    double mcm_scaling;         /* spec["mcm_scaling"] (:265)                                        */
+    double risk_aversion;       /* spec["risk_aversion"] (:836,:849)                                 */
+    int prior_weights;          /* 0: value weighted ("vw" in strategy, :369) 1: equally weighted    */
+} bp_window_batch;
+
+/* Optional outputs (NULL = not wanted).  Vectors are [W][N], matrices [W][N][N] dense symmetric. */
+typedef struct {
+    double* weights;            /* (1/gamma) nu                  :836 / :849                         */
+    double* nu;                 /* posterior mean nu             :572-575 / :606                     */
+    double* w1;                 /* conjugate posterior w         :489 (Jeffreys: same as nu)         */
+    double* t;                  /* canonical statistic t         :222                                */
+    double* w0;                 /* prior weights                 :361-380                            */
+    double* rhs;                /* c S0 w0 + t                   :489                                */
+    double* scalars;            /* [W][BP_NSCAL]                                                     */
+    int* status;                /* [W] 0 ok; k+1: pivot k not positive (reference would return garbage, F6) */
+    double* T;                  /* canonical statistic T         :180-182                            */
+    double* S0;                 /* conjugate prior S             :333                                */
+    double* S1;                 /* posterior S (or Jeffreys J)   :358 / :600-601                     */
+} bp_outputs;
+
+const char* bp_last_error(void);
+int bp_version(void);
+
+/* Create / destroy a context on CUDA device `device`.  Fails with BP_ERR_NO_DEVICE when there is no
+ * sm_100 GPU: there is no CPU path. */
+int bp_init(int device, bp_handle** out);
+int bp_destroy(bp_handle* h);
+/* Launch on the caller's CUDA stream (a cudaStream_t), e.g. torch's current stream. */
+int bp_set_stream(bp_handle* h, void* cuda_stream);
+int bp_synchronize(bp_handle* h);
+/* Upper bound for the per-batch workspace (bytes); windows are processed in chunks that fit. */
+int bp_set_workspace_limit(bp_handle* h, size_t bytes);
+int bp_device_info(bp_handle* h, int* sm_count, size_t* free_bytes, size_t* total_bytes);
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+long long bp_launch_count(bp_handle* h);
+
+/* Host -> HBM: replaces the pandas frames of get_market_data() (data_handling.py:270-291).  Also
+ * computes both log-return matrices on the device (:37, :314). */
+int bp_upload_market(bp_handle* h, const bp_market_desc* m);
+/* Re-run the log-return stage on the resident prices (device-only timing of the whole path). */
+int bp_prepare_market(bp_handle* h);
+
+/* calculate_canonical_statistics_t / _T (:163-245) for W windows. t:[W][N], T:[W][N][N]. */
+int bp_stats_batched(bp_handle* h, const bp_window_batch* b, double* t, double* T);
+/* calculate_conjugate_prior_n / _S (:247-267, :285-333): n0:[W], S0:[W][N][N] (= n0 * cov * m). */
+int bp_hf_cov_batched(bp_handle* h, const bp_window_batch* b, double* n0, double* S0);
+/* calculate_conjugate_hf_mcm_portfolio (:819-836) for W windows. */
+int bp_conjugate_batched(bp_handle* h, const bp_window_batch* b, const bp_outputs* out);
+/* calculate_jeffreys_portfolio (:838-849) for W windows. */
+int bp_jeffreys_batched(bp_handle* h, const bp_window_batch* b, const bp_outputs* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYES_PORTFOLIO_H */

@@ -1,0 +1,93 @@
+"""ctypes binding of ``libbayes_portfolio.so`` (see ``include/bayes_portfolio.h``).
+
+The library is the product: there is no CPU fallback.  Loading works without a GPU (so that the
+CPU test-suite can check the exported symbols), but ``bp_init`` fails loudly when no sm_100 device
+is present, and every engine call raises if the library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbayes_portfolio.so")
+
+BP_NSCAL = 12
+SCAL = dict(n0=0, n1=1, alpha=2, beta=3, c=4, v0=5, m=6, sum_a=7, v1=8)
+
+BP_OK, BP_ERR_INVALID, BP_ERR_CUDA, BP_ERR_NO_DEVICE, BP_ERR_STATE = 0, 1, 2, 3, 4
+
+EXPORTED = [
+    "bp_last_error", "bp_version", "bp_init", "bp_destroy", "bp_set_stream", "bp_synchronize",
+    "bp_set_workspace_limit", "bp_device_info", "bp_launch_count", "bp_upload_market",
+    "bp_prepare_market", "bp_stats_batched", "bp_hf_cov_batched", "bp_conjugate_batched",
+    "bp_jeffreys_batched",
+]
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+
+class MarketDesc(C.Structure):
+    _fields_ = [
+        ("n_assets", C.c_int), ("n_days", C.c_int), ("n_hf_rows", C.c_longlong),
+        ("prices", C.c_void_p), ("caps", C.c_void_p), ("hf_prices", C.c_void_p),
+        ("mcm", C.c_void_p), ("n_mcm", C.c_int), ("rf_row", C.c_void_p),
+    ]
+
+
+class WindowBatchDesc(C.Structure):
+    _fields_ = [
+        ("n_windows", C.c_int), ("rolling_window", C.c_int),
+        ("day_row", C.c_void_p), ("span_days", C.c_void_p), ("hf_lo", C.c_void_p), ("hf_hi", C.c_void_p),
+        ("mcm_index", C.c_int), ("mcm_scaling", C.c_double), ("risk_aversion", C.c_double),
+        ("prior_weights", C.c_int),
+    ]
+
+
+class Outputs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in
+                ("weights", "nu", "w1", "t", "w0", "rhs", "scalars", "status", "T", "S0", "S1")]
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building is the job of ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            f"{LIB_PATH} is missing: build it with `python -m incorporating_different_sources_b200.build` "
+            "(there is no CPU fallback for the CUDA path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.bp_last_error.restype = C.c_char_p
+    lib.bp_version.restype = C.c_int
+    lib.bp_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.bp_destroy.argtypes = [C.c_void_p]
+    lib.bp_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bp_synchronize.argtypes = [C.c_void_p]
+    lib.bp_set_workspace_limit.argtypes = [C.c_void_p, C.c_size_t]
+    lib.bp_device_info.argtypes = [C.c_void_p, c_int_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.bp_launch_count.argtypes = [C.c_void_p]
+    lib.bp_launch_count.restype = C.c_longlong
+    lib.bp_upload_market.argtypes = [C.c_void_p, C.POINTER(MarketDesc)]
+    lib.bp_prepare_market.argtypes = [C.c_void_p]
+    lib.bp_stats_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.c_void_p, C.c_void_p]
+    lib.bp_hf_cov_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.c_void_p, C.c_void_p]
+    lib.bp_conjugate_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.POINTER(Outputs)]
+    lib.bp_jeffreys_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.POINTER(Outputs)]
+    for name in EXPORTED:
+        getattr(lib, name)          # every declared entry point must be exported
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().bp_last_error().decode("utf-8", "replace")

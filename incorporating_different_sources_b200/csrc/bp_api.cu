@@ -1,0 +1,610 @@
+// C-ABI of libbayes_portfolio.so: market residency, window batches, stage orchestration.
+// Declarations and the reference interfaces each entry point replaces: include/bayes_portfolio.h.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bayes_portfolio.h"
+#include "kernels.h"
+
+using namespace bp;
+
+static_assert(BP_NSCAL == bp::BP_S_COUNT, "scalar record size mismatch between header and kernels");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                     \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(BP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+struct bp_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    size_t ws_limit = (size_t)24 << 30;
+    long long launches = 0;
+    // market
+    bool has_market = false;
+    int N = 0, D = 0, ld = 0, n_mcm = 0;
+    long long R = 0;
+    double *prices = nullptr, *lr_d = nullptr, *caps = nullptr, *hf_prices = nullptr, *lr_hf = nullptr,
+           *mcm = nullptr, *rf_row = nullptr;
+    CUtensorMap map_d, map_hf;
+    // window descriptors on the device: day_row, span, row0, hf_row0, hf_m
+    int* desc = nullptr;
+    int desc_cap = 0;
+    // workspace
+    unsigned char* ws = nullptr;
+    size_t ws_bytes = 0;
+    unsigned char* stage = nullptr;
+    size_t stage_bytes = 0;
+    bool need_sync = false;
+    PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+};
+
+namespace {
+
+void free_market(bp_handle* h) {
+    cudaFree(h->prices); cudaFree(h->lr_d); cudaFree(h->caps); cudaFree(h->hf_prices);
+    cudaFree(h->lr_hf); cudaFree(h->mcm); cudaFree(h->rf_row);
+    h->prices = h->lr_d = h->caps = h->hf_prices = h->lr_hf = h->mcm = h->rf_row = nullptr;
+    h->has_market = false;
+}
+
+int make_map(bp_handle* h, CUtensorMap* map, const double* base, long long rows, int ld) {
+    // 3-D view (16-column group element, row, column group) of a row-major [rows][ld] matrix
+    cuuint64_t dims[3] = {16, (cuuint64_t)rows, (cuuint64_t)(ld / 16)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(double), 16 * sizeof(double)};
+    cuuint32_t box[3] = {16, (cuuint32_t)GRAM_KT, 8};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(BP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return BP_OK;
+}
+
+int ensure_ws(bp_handle* h, size_t bytes) {
+    if (bytes <= h->ws_bytes) return BP_OK;
+    if (h->ws) cudaFree(h->ws);
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+    CU_TRY(cudaMalloc(&h->ws, bytes));
+    h->ws_bytes = bytes;
+    return BP_OK;
+}
+
+int ensure_stage(bp_handle* h, size_t bytes) {
+    if (bytes <= h->stage_bytes) return BP_OK;
+    if (h->stage) {
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        cudaFree(h->stage);
+    }
+    h->stage = nullptr;
+    h->stage_bytes = 0;
+    CU_TRY(cudaMalloc(&h->stage, bytes));
+    h->stage_bytes = bytes;
+    return BP_OK;
+}
+
+struct Chunk {
+    // carved from the workspace for Wc windows
+    double *S, *t, *pvec, *gvec, *rhs, *w0, *s0w0, *w1, *nu, *weights, *scal, *y;
+    int* status;
+};
+
+struct Layout {
+    int N, ldv, ldS, rowsS;
+    long long win_stride, y_stride;
+    size_t per_window;
+};
+
+Layout make_layout(const bp_handle* h, int max_m) {
+    Layout L;
+    L.N = h->N;
+    L.ldv = h->ld;
+    L.ldS = round_up(h->N, 32);
+    L.rowsS = L.ldS + 8;
+    L.win_stride = (long long)L.rowsS * L.ldS;
+    L.y_stride = round_up(std::max(max_m, 2), 2);
+    L.per_window = sizeof(double) * ((size_t)L.win_stride + 9 * (size_t)L.ldv + BP_NSCAL + (size_t)L.y_stride) + 16;
+    return L;
+}
+
+Chunk carve(unsigned char* ws, const Layout& L, int Wc) {
+    Chunk c;
+    double* p = reinterpret_cast<double*>(ws);
+    c.S = p;        p += (size_t)Wc * L.win_stride;
+    c.t = p;        p += (size_t)Wc * L.ldv;
+    c.pvec = p;     p += (size_t)Wc * L.ldv;
+    c.gvec = p;     p += (size_t)Wc * L.ldv;
+    c.rhs = p;      p += (size_t)Wc * L.ldv;
+    c.w0 = p;       p += (size_t)Wc * L.ldv;
+    c.s0w0 = p;     p += (size_t)Wc * L.ldv;
+    c.w1 = p;       p += (size_t)Wc * L.ldv;
+    c.nu = p;       p += (size_t)Wc * L.ldv;
+    c.weights = p;  p += (size_t)Wc * L.ldv;
+    c.scal = p;     p += (size_t)Wc * BP_NSCAL;
+    c.y = p;        p += (size_t)Wc * L.y_stride;
+    c.status = reinterpret_cast<int*>(p);
+    return c;
+}
+
+// validated, device-resident description of one batch
+struct Batch {
+    int W = 0, n = 0, max_m = 0;
+    bool has_hf = false;
+    const int *day_row = nullptr, *span = nullptr, *row0 = nullptr, *hf_row0 = nullptr, *hf_m = nullptr;
+};
+
+int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* out) {
+    if (!h || !b) return fail(BP_ERR_INVALID, "null handle or batch");
+    if (!h->has_market) return fail(BP_ERR_STATE, "no market uploaded: call bp_upload_market first");
+    const int W = b->n_windows, n = b->rolling_window;
+    if (W <= 0) return fail(BP_ERR_INVALID, "n_windows must be positive");
+    if (n < 3) return fail(BP_ERR_INVALID, "rolling_window must be >= 3");
+    if (!b->day_row || !b->span_days) return fail(BP_ERR_INVALID, "day_row / span_days missing");
+    if (need_hf) {
+        if (!b->hf_lo || !b->hf_hi) return fail(BP_ERR_INVALID, "hf_lo / hf_hi missing");
+        if (h->R <= 0) return fail(BP_ERR_STATE, "the uploaded market has no intraday prices");
+        if (b->mcm_index < 0 || b->mcm_index >= h->n_mcm) return fail(BP_ERR_INVALID, "mcm_index %d out of range", b->mcm_index);
+        if (b->prior_weights == 0 && !h->caps) return fail(BP_ERR_STATE, "value-weighted prior needs market caps");
+    }
+    std::vector<int> host((size_t)5 * W, 0);
+    int max_m = 0;
+    for (int w = 0; w < W; ++w) {
+        const int dr = b->day_row[w];
+        if (dr < n - 1 || dr >= h->D)
+            return fail(BP_ERR_INVALID, "window %d: day_row %d needs %d prior price rows inside [0,%d)", w, dr, n - 1, h->D);
+        if (b->span_days[w] <= 0) return fail(BP_ERR_INVALID, "window %d: span_days must be positive", w);
+        host[w] = dr;
+        host[(size_t)W + w] = b->span_days[w];
+        host[(size_t)2 * W + w] = dr - n + 2;       // first daily RETURN row (F2: n prices -> n-1 returns)
+        if (need_hf) {
+            const int lo = b->hf_lo[w], hi = b->hf_hi[w];
+            const int m = hi - lo - 1;
+            if (lo < 0 || (long long)hi > h->R || m < 2)
+                return fail(BP_ERR_INVALID, "window %d: intraday rows [%d,%d) give %d returns (need >= 2, rows < %lld)", w, lo, hi, m, h->R);
+            host[(size_t)3 * W + w] = lo + 1;        // first HF return row: the window's first bar has no return (F5)
+            host[(size_t)4 * W + w] = m;
+            max_m = std::max(max_m, m);
+        }
+    }
+    if (W > h->desc_cap) {
+        if (h->desc) {
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            cudaFree(h->desc);
+        }
+        h->desc = nullptr;
+        h->desc_cap = 0;
+        CU_TRY(cudaMalloc(&h->desc, sizeof(int) * 5 * (size_t)W));
+        h->desc_cap = W;
+    }
+    // the staging vector dies at return: make the copy complete before that
+    CU_TRY(cudaMemcpyAsync(h->desc, host.data(), sizeof(int) * 5 * (size_t)W, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    out->W = W;
+    out->n = n;
+    out->max_m = max_m;
+    out->has_hf = need_hf;
+    out->day_row = h->desc;
+    out->span = h->desc + W;
+    out->row0 = h->desc + 2 * (size_t)W;
+    out->hf_row0 = h->desc + 3 * (size_t)W;
+    out->hf_m = h->desc + 4 * (size_t)W;
+    return BP_OK;
+}
+
+// dense [Wc][N] copy of a strided device vector to a host or device destination
+int emit_vec(bp_handle* h, const double* src, const Layout& L, int Wc, double* dst) {
+    if (!dst) return BP_OK;
+    if (is_device_ptr(dst)) {
+        launch_unpack_vec(src, L.ldv, L.N, Wc, dst, h->stream);
+        h->launches++;
+    } else {
+        const size_t bytes = sizeof(double) * (size_t)Wc * L.N;
+        // the single staging buffer is reused: drain the previous D2H copy before overwriting it
+        if (h->need_sync) CU_TRY(cudaStreamSynchronize(h->stream));
+        int rc = ensure_stage(h, bytes);
+        if (rc) return rc;
+        launch_unpack_vec(src, L.ldv, L.N, Wc, reinterpret_cast<double*>(h->stage), h->stream);
+        h->launches++;
+        CU_TRY(cudaMemcpyAsync(dst, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+        h->need_sync = true;
+    }
+    return BP_OK;
+}
+
+int emit_sym(bp_handle* h, const double* S, const Layout& L, int Wc, double* dst) {
+    if (!dst) return BP_OK;
+    if (is_device_ptr(dst)) {
+        launch_unpack_sym(S, L.win_stride, L.ldS, L.N, Wc, dst, h->stream);
+        h->launches++;
+    } else {
+        const size_t bytes = sizeof(double) * (size_t)Wc * L.N * L.N;
+        if (h->need_sync) CU_TRY(cudaStreamSynchronize(h->stream));
+        int rc = ensure_stage(h, bytes);
+        if (rc) return rc;
+        launch_unpack_sym(S, L.win_stride, L.ldS, L.N, Wc, reinterpret_cast<double*>(h->stage), h->stream);
+        h->launches++;
+        CU_TRY(cudaMemcpyAsync(dst, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+        h->need_sync = true;
+    }
+    return BP_OK;
+}
+
+int emit_raw(bp_handle* h, const void* src, size_t bytes, void* dst) {
+    if (!dst) return BP_OK;
+    const bool dev = is_device_ptr(dst);
+    CU_TRY(cudaMemcpyAsync(dst, src, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    if (!dev) h->need_sync = true;
+    return BP_OK;
+}
+
+PrepParams prep_params(const bp_handle* h, const bp_window_batch* b, const Batch& B, const Layout& L, const Chunk& c,
+                       int w0, int mode) {
+    PrepParams p{};
+    p.mode = mode;
+    p.n_assets = h->N;
+    p.n_window = B.n;
+    p.ld = h->ld;
+    p.ldv = L.ldv;
+    p.prior_kind = b->prior_weights == 0 ? BP_PRIOR_VW : BP_PRIOR_EW;
+    p.mcm_scaling = b->mcm_scaling;
+    p.lr_daily = h->lr_d;
+    p.lr_hf = h->lr_hf;
+    p.caps = h->caps;
+    p.mcm = (mode == BP_MODE_CONJUGATE) ? h->mcm + (size_t)b->mcm_index * h->D : nullptr;
+    p.rf_row = h->rf_row;
+    p.day_row = B.day_row + w0;
+    p.span_days = B.span + w0;
+    p.hf_row0 = B.hf_row0 + w0;
+    p.hf_m = B.hf_m + w0;
+    p.t = c.t; p.pvec = c.pvec; p.gvec = c.gvec; p.rhs = c.rhs; p.w0 = c.w0; p.s0w0 = c.s0w0;
+    p.scal = c.scal;
+    p.y_ws = c.y;
+    p.y_stride = L.y_stride;
+    return p;
+}
+
+enum GramKind { GRAM_T, GRAM_S0, GRAM_S1, GRAM_J };
+
+GramParams gram_params(const bp_handle* h, const Batch& B, const Layout& L, const Chunk& c, int w0, int Wc, GramKind kind) {
+    GramParams g{};
+    g.n_windows = Wc;
+    g.n_assets = h->N;
+    g.ldS = L.ldS;
+    g.win_stride = L.win_stride;
+    g.ldv = L.ldv;
+    g.mirror = 0;
+    g.scal = c.scal;
+    g.out = c.S;
+    const bool hf = kind == GRAM_S0 || kind == GRAM_S1;
+    const bool daily = kind != GRAM_S0;
+    if (hf) {
+        g.seg0_row0 = B.hf_row0 + w0;
+        g.seg0_rows = B.hf_m + w0;
+        g.use_alpha = 1;
+        g.use_beta = 1;          // beta = alpha*m, g = hbar
+        g.gvec = c.gvec;
+    }
+    if (daily) {
+        g.seg1_row0 = B.row0 + w0;
+        g.seg1_rows = nullptr;
+        g.seg1_rows_const = B.n - 1;
+        g.pvec = c.pvec;
+    }
+    if (kind == GRAM_J) {
+        g.use_beta = 1;          // beta = 1/n, g = t
+        g.gvec = c.gvec;
+    }
+    return g;
+}
+
+int run_gram(bp_handle* h, const GramParams& g) {
+    CU_TRY(launch_gram(g, h->map_hf, h->map_d, h->sm_count, h->stream));
+    h->launches++;
+    return BP_OK;
+}
+
+int finish(bp_handle* h) {
+    if (h->need_sync) {
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        h->need_sync = false;
+    }
+    return BP_OK;
+}
+
+// shared driver of bp_conjugate_batched / bp_jeffreys_batched / bp_stats_batched / bp_hf_cov_batched
+int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, int mode, bool solve) {
+    Batch B;
+    int rc = upload_batch(h, b, mode == BP_MODE_CONJUGATE, &B);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(h->device));
+    const Layout L = make_layout(h, B.max_m);
+    int Wc = (int)std::min<size_t>((size_t)B.W, std::max<size_t>(1, h->ws_limit / L.per_window));
+    rc = ensure_ws(h, (size_t)Wc * L.per_window + 256);
+    if (rc) return rc;
+    const Chunk c = carve(h->ws, L, Wc);
+    const int N = h->N;
+    if (solve && mode == BP_MODE_CONJUGATE && !(b->risk_aversion != 0.0))
+        return fail(BP_ERR_INVALID, "risk_aversion must be non-zero");
+
+    for (int w0 = 0; w0 < B.W; w0 += Wc) {
+        const int wc = std::min(Wc, B.W - w0);
+        const size_t ov = (size_t)w0 * N, om = (size_t)w0 * N * N;
+        PrepParams pp = prep_params(h, b, B, L, c, w0, mode);
+        CU_TRY(launch_window_prep(pp, wc, h->stream));
+        h->launches++;
+        if (out->T) {
+            rc = run_gram(h, gram_params(h, B, L, c, w0, wc, GRAM_T));
+            if (rc) return rc;
+            rc = emit_sym(h, c.S, L, wc, out->T + om);
+            if (rc) return rc;
+        }
+        if (out->S0 && mode == BP_MODE_CONJUGATE) {
+            rc = run_gram(h, gram_params(h, B, L, c, w0, wc, GRAM_S0));
+            if (rc) return rc;
+            rc = emit_sym(h, c.S, L, wc, out->S0 + om);
+            if (rc) return rc;
+        }
+        if (solve || out->S1) {
+            rc = run_gram(h, gram_params(h, B, L, c, w0, wc, mode == BP_MODE_CONJUGATE ? GRAM_S1 : GRAM_J));
+            if (rc) return rc;
+            rc = emit_sym(h, c.S, L, wc, out->S1 ? out->S1 + om : nullptr);
+            if (rc) return rc;
+        }
+        if (solve) {
+            SolveParams sp{};
+            sp.n_windows = wc;
+            sp.n_assets = N;
+            sp.ldS = L.ldS;
+            sp.win_stride = L.win_stride;
+            sp.ldv = L.ldv;
+            sp.mode = mode;
+            sp.inv_gamma = 1.0 / b->risk_aversion;         // the reference evaluates (1/gamma) * nu (:836,:849)
+            sp.S = c.S;
+            sp.rhs = c.rhs;
+            sp.scal = c.scal;
+            sp.w1 = c.w1;
+            sp.nu = c.nu;
+            sp.weights = c.weights;
+            sp.status = c.status;
+            CU_TRY(launch_chol_solve(sp, h->sm_count, h->stream));
+            h->launches++;
+            if ((rc = emit_vec(h, c.weights, L, wc, out->weights ? out->weights + ov : nullptr))) return rc;
+            if ((rc = emit_vec(h, c.nu, L, wc, out->nu ? out->nu + ov : nullptr))) return rc;
+            if ((rc = emit_vec(h, c.w1, L, wc, out->w1 ? out->w1 + ov : nullptr))) return rc;
+            if ((rc = emit_raw(h, c.status, sizeof(int) * (size_t)wc, out->status ? out->status + w0 : nullptr))) return rc;
+        }
+        if ((rc = emit_vec(h, c.t, L, wc, out->t ? out->t + ov : nullptr))) return rc;
+        if (mode == BP_MODE_CONJUGATE) {
+            if ((rc = emit_vec(h, c.w0, L, wc, out->w0 ? out->w0 + ov : nullptr))) return rc;
+        }
+        if ((rc = emit_vec(h, c.rhs, L, wc, out->rhs ? out->rhs + ov : nullptr))) return rc;
+        if ((rc = emit_raw(h, c.scal, sizeof(double) * (size_t)wc * BP_NSCAL,
+                           out->scalars ? out->scalars + (size_t)w0 * BP_NSCAL : nullptr))) return rc;
+        // the workspace is reused by the next chunk: host-bound copies must have drained
+        if (w0 + wc < B.W && h->need_sync) {
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            h->need_sync = false;
+        }
+    }
+    return finish(h);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bp_last_error(void) { return g_err.c_str(); }
+int bp_version(void) { return 100; }
+
+int bp_init(int device, bp_handle** out) {
+    if (!out) return fail(BP_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(BP_ERR_NO_DEVICE, "no CUDA device visible: libbayes_portfolio has no CPU path");
+    }
+    if (device < 0 || device >= count) return fail(BP_ERR_INVALID, "device %d out of range (%d visible)", device, count);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(BP_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    CU_TRY(cudaSetDevice(device));
+    bp_handle* h = new bp_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        delete h;
+        return fail(BP_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    }
+    h->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    *out = h;
+    return BP_OK;
+}
+
+int bp_destroy(bp_handle* h) {
+    if (!h) return BP_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_market(h);
+    cudaFree(h->desc);
+    cudaFree(h->ws);
+    cudaFree(h->stage);
+    delete h;
+    return BP_OK;
+}
+
+int bp_set_stream(bp_handle* h, void* cuda_stream) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return BP_OK;
+}
+
+int bp_synchronize(bp_handle* h) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return BP_OK;
+}
+
+int bp_set_workspace_limit(bp_handle* h, size_t bytes) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    h->ws_limit = bytes;
+    return BP_OK;
+}
+
+int bp_device_info(bp_handle* h, int* sm_count, size_t* free_bytes, size_t* total_bytes) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    CU_TRY(cudaSetDevice(h->device));
+    size_t f = 0, t = 0;
+    CU_TRY(cudaMemGetInfo(&f, &t));
+    if (sm_count) *sm_count = h->sm_count;
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return BP_OK;
+}
+
+long long bp_launch_count(bp_handle* h) { return h ? h->launches : 0; }
+
+int bp_prepare_market(bp_handle* h) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    if (!h->has_market) return fail(BP_ERR_STATE, "no market uploaded");
+    CU_TRY(cudaSetDevice(h->device));
+    launch_log_returns(h->prices, h->lr_d, h->D, h->N, h->ld, h->sm_count, h->stream);
+    h->launches++;
+    if (h->R > 0) {
+        launch_log_returns(h->hf_prices, h->lr_hf, h->R, h->N, h->ld, h->sm_count, h->stream);
+        h->launches++;
+    }
+    CU_TRY(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_upload_market(bp_handle* h, const bp_market_desc* m) {
+    if (!h || !m) return fail(BP_ERR_INVALID, "null handle or market");
+    if (m->n_assets <= 0 || m->n_days < 2 || !m->prices || !m->rf_row)
+        return fail(BP_ERR_INVALID, "market needs n_assets > 0, n_days >= 2, prices and rf_row");
+    if (m->n_hf_rows < 0 || (m->n_hf_rows > 0 && !m->hf_prices)) return fail(BP_ERR_INVALID, "hf_prices missing");
+    if (m->n_hf_rows > 0x7fffffffLL) return fail(BP_ERR_INVALID, "too many intraday rows for int32 row indices");
+    if (m->n_mcm < 0 || (m->n_mcm > 0 && !m->mcm)) return fail(BP_ERR_INVALID, "mcm missing");
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    free_market(h);
+    const int N = m->n_assets, D = m->n_days, ld = round_up(N, 16);
+    const long long R = m->n_hf_rows;
+    h->N = N; h->D = D; h->ld = ld; h->R = R; h->n_mcm = m->n_mcm;
+    const size_t drow = sizeof(double) * (size_t)ld, srow = sizeof(double) * (size_t)N;
+    auto upload2d = [&](double** dst, const double* src, long long rows) -> int {
+        CU_TRY(cudaMalloc(dst, drow * (size_t)rows));
+        if (ld > N)
+            CU_TRY(cudaMemset2DAsync(*dst + N, drow, 0, drow - srow, (size_t)rows, h->stream));
+        CU_TRY(cudaMemcpy2DAsync(*dst, drow, src, srow, srow, (size_t)rows, cudaMemcpyHostToDevice, h->stream));
+        return BP_OK;
+    };
+    int rc;
+    if ((rc = upload2d(&h->prices, m->prices, D))) return rc;
+    CU_TRY(cudaMalloc(&h->lr_d, drow * (size_t)D));
+    if (m->caps && (rc = upload2d(&h->caps, m->caps, D))) return rc;
+    if (R > 0) {
+        if ((rc = upload2d(&h->hf_prices, m->hf_prices, R))) return rc;
+        CU_TRY(cudaMalloc(&h->lr_hf, drow * (size_t)R));
+    }
+    if (m->n_mcm > 0) {
+        CU_TRY(cudaMalloc(&h->mcm, sizeof(double) * (size_t)m->n_mcm * D));
+        CU_TRY(cudaMemcpyAsync(h->mcm, m->mcm, sizeof(double) * (size_t)m->n_mcm * D, cudaMemcpyHostToDevice, h->stream));
+    }
+    CU_TRY(cudaMalloc(&h->rf_row, sizeof(double) * (size_t)D));
+    CU_TRY(cudaMemcpyAsync(h->rf_row, m->rf_row, sizeof(double) * (size_t)D, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = make_map(h, &h->map_d, h->lr_d, D, ld))) return rc;
+    if (R > 0) {
+        if ((rc = make_map(h, &h->map_hf, h->lr_hf, R, ld))) return rc;
+    } else {
+        h->map_hf = h->map_d;
+    }
+    h->has_market = true;
+    rc = bp_prepare_market(h);
+    if (rc) return rc;
+    // the caller's host arrays may be pageable and may be freed after return
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return BP_OK;
+}
+
+int bp_conjugate_batched(bp_handle* h, const bp_window_batch* b, const bp_outputs* out) {
+    if (!out) return fail(BP_ERR_INVALID, "outputs missing");
+    return run_batches(h, b, out, BP_MODE_CONJUGATE, true);
+}
+
+int bp_jeffreys_batched(bp_handle* h, const bp_window_batch* b, const bp_outputs* out) {
+    if (!out) return fail(BP_ERR_INVALID, "outputs missing");
+    return run_batches(h, b, out, BP_MODE_JEFFREYS, true);
+}
+
+int bp_stats_batched(bp_handle* h, const bp_window_batch* b, double* t, double* T) {
+    bp_outputs o;
+    memset(&o, 0, sizeof(o));
+    o.t = t;
+    o.T = T;
+    return run_batches(h, b, &o, BP_MODE_JEFFREYS, false);
+}
+
+int bp_hf_cov_batched(bp_handle* h, const bp_window_batch* b, double* n0, double* S0) {
+    if (!h || !b) return fail(BP_ERR_INVALID, "null handle or batch");
+    bp_outputs o;
+    memset(&o, 0, sizeof(o));
+    o.S0 = S0;
+    std::vector<double> scal;
+    if (n0) {
+        scal.resize((size_t)std::max(b->n_windows, 0) * BP_NSCAL);
+        o.scalars = scal.data();
+    }
+    int rc = run_batches(h, b, &o, BP_MODE_CONJUGATE, false);
+    if (rc) return rc;
+    if (n0) {
+        if (is_device_ptr(n0)) return fail(BP_ERR_INVALID, "bp_hf_cov_batched: n0 must be a host pointer");
+        for (int w = 0; w < b->n_windows; ++w) n0[w] = scal[(size_t)w * BP_NSCAL + BP_SCAL_N0];
+    }
+    return BP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// Internal launch interfaces shared by the .cu translation units (not part of the C-ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace bp {
+
+enum { BP_MODE_CONJUGATE = 0, BP_MODE_JEFFREYS = 1 };
+enum { BP_PRIOR_VW = 0, BP_PRIOR_EW = 1 };
+
+// per-window scalar record written by window_prep_kernel / chol_solve_kernel
+enum {
+    BP_S_N0 = 0,     // conjugate prior n            (:265)
+    BP_S_N1 = 1,     // posterior n                  (:282)
+    BP_S_ALPHA = 2,  // n0 * m/(m-1): scale of the raw HF Gram inside S0
+    BP_S_BETA = 3,   // rank-1 coefficient of the Gram epilogue (alpha*m, or 1/n for Jeffreys)
+    BP_S_C = 4,      // conjugate c                  (:415-418)
+    BP_S_V0 = 5,     // w0' S0 w0                    (:78)
+    BP_S_M = 6,      // HF returns in the window
+    BP_S_SUMA = 7,   // sum_k a_k
+    BP_S_V1 = 8,     // w1' S1 w1                    (:574)
+    BP_S_COUNT = 12
+};
+
+struct PrepParams {
+    int mode;            // BP_MODE_*
+    int n_assets;        // N
+    int n_window;        // rolling_window n (prices); n-1 returns
+    int ld;              // leading dimension of the market matrices
+    int ldv;             // leading dimension of the per-window vectors
+    int prior_kind;      // BP_PRIOR_*
+    double mcm_scaling;
+    const double* lr_daily;   // [D][ld] daily log returns (row r = log(P_r / P_{r-1}))
+    const double* lr_hf;      // [R][ld] intraday log returns
+    const double* caps;       // [D][ld]
+    const double* mcm;        // [D]
+    const double* rf_row;     // [D] risk-free forward-filled onto the daily rows
+    const int* day_row;       // [W]
+    const int* span_days;     // [W]
+    const int* hf_row0;       // [W] first intraday RETURN row of the HF window (= first price row + 1)
+    const int* hf_m;          // [W] number of HF returns m
+    double* t;                // [W][ldv]
+    double* pvec;             // [W][ldv]  u - a'a/2
+    double* gvec;             // [W][ldv]  hbar (conjugate) or t (Jeffreys)
+    double* rhs;              // [W][ldv]  b = c S0 w0 + t   (or t)
+    double* w0;               // [W][ldv]
+    double* s0w0;             // [W][ldv]
+    double* scal;             // [W][BP_NSCAL]
+    double* y_ws;             // [W][y_stride] scratch for the HF row dots
+    long long y_stride;
+};
+
+struct GramParams {
+    int n_windows;
+    int n_assets;        // N
+    int ldS;             // leading dimension of the output matrices
+    long long win_stride;    // doubles between consecutive output matrices
+    int ldv;
+    int mirror;          // also write the upper triangle
+    // segment 0 (HF returns; scaled by alpha afterwards) and segment 1 (daily returns)
+    const int* seg0_row0;    // [W] first row of segment 0 in tensor map 0 (nullptr: no segment 0)
+    const int* seg0_rows;    // [W]
+    const int* seg1_row0;    // [W] (nullptr: no segment 1)
+    const int* seg1_rows;    // [W]
+    int seg0_row_bias;       // added to seg0_row0[w]
+    int seg0_rows_bias;      // added to seg0_rows[w]
+    int seg1_row_bias;
+    int seg1_rows_const;     // if seg1_rows == nullptr: constant row count
+    const double* scal;      // [W][BP_NSCAL] (alpha, beta) ; nullptr -> alpha = 1, beta = 0
+    int use_alpha;
+    int use_beta;
+    const double* pvec;      // [W][ldv] or nullptr
+    const double* gvec;      // [W][ldv] or nullptr
+    double* out;             // [W][win_stride]
+};
+
+struct SolveParams {
+    int n_windows;
+    int n_assets;
+    int ldS;
+    long long win_stride;
+    int ldv;
+    int mode;                // BP_MODE_*
+    double inv_gamma;        // 1 / risk_aversion
+    double* S;               // [W][win_stride] in: lower triangle of S1 / J ; out: Cholesky factor
+    const double* rhs;       // [W][ldv]
+    double* scal;            // [W][BP_NSCAL]  (reads n1, writes v1)
+    double* w1;              // [W][ldv] posterior w  (S^-1 rhs)
+    double* nu;              // [W][ldv]
+    double* weights;         // [W][ldv]
+    int* status;             // [W] 0 = ok, k+1 = non-positive pivot at column k
+};
+
+void launch_log_returns(const double* P, double* out, long long rows, int n_assets, int ld, int sm_count,
+                        cudaStream_t st);
+size_t prep_smem_bytes(int n_window, int ldv);
+cudaError_t launch_window_prep(const PrepParams& p, int n_windows, cudaStream_t st);
+void launch_unpack_sym(const double* S, long long win_stride, int ldS, int N, int W, double* out, cudaStream_t st);
+void launch_unpack_vec(const double* v, int ldv, int N, long long W, double* out, cudaStream_t st);
+
+// Gram (DMMA + TMA)
+constexpr int GRAM_KT = 32;        // rows per TMA k-tile
+constexpr int GRAM_TILE = 128;     // output tile edge
+cudaError_t launch_gram(const GramParams& p, const CUtensorMap& map0, const CUtensorMap& map1, int sm_count,
+                        cudaStream_t st);
+cudaError_t launch_chol_solve(const SolveParams& p, int sm_count, cudaStream_t st);
+
+}  // namespace bp

@@ -1,0 +1,314 @@
+// Streaming (HBM / L2 bound) stages of the path.
+//
+//  * log_returns_kernel        : prices -> log(P_i / P_{i-1})           (portfolio_calculations.py:37, :314)
+//  * window_prep_kernel        : per rebalance window, everything that is O(N*K):
+//      a_k, t, u            (:40-57, :222)        excess-return column sums via the rank-2 form
+//      n0, n1               (:90-114, :247-282)   MCM (VIX/EPU) scaling of the prior
+//      w0                   (:361-380, :661-701)  value / equal prior weights
+//      hbar, S0*w0, v0      (:314-318, :64-88)    HF realised-covariance mean terms, w0'S0w0
+//      c, b = c*S0*w0 + t   (:415-418, :489)      conjugate scalar and right-hand side
+//  * pack / unpack helpers between the padded device layout and dense N x N outputs.
+//
+// The excess-return matrix X_w = L - a_w 1' differs per window, but the Gram matrix
+// never needs X_w explicitly:  T = L'L - u 1' - 1 u' + (a'a) 11',  u = L'a,  t = L'1 - (sum a) 1.
+// The window_prep kernel produces p = u - (a'a)/2 so that T_ij = (L'L)_ij - p_i - p_j, which the
+// Gram kernel applies in its epilogue; the shared log-return matrix L is then TMA-loadable by
+// every overlapping window.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bp {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void log_returns_kernel(const double* __restrict__ P, double* __restrict__ out, long long rows,
+                                   int n_assets, int ld) {
+    const long long half = ld >> 1;
+    const long long total = rows * half;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / half;
+        const int c = int(i - r * half) * 2;
+        double2 o = make_double2(0.0, 0.0);
+        if (r > 0) {
+            const double2 p = *reinterpret_cast<const double2*>(P + r * ld + c);
+            const double2 q = *reinterpret_cast<const double2*>(P + (r - 1) * ld + c);
+            if (c < n_assets) o.x = log(p.x / q.x);
+            if (c + 1 < n_assets) o.y = log(p.y / q.y);
+        }
+        *reinterpret_cast<double2*>(out + r * ld + c) = o;
+    }
+}
+
+void launch_log_returns(const double* P, double* out, long long rows, int n_assets, int ld, int sm_count,
+                        cudaStream_t st) {
+    if (rows <= 0) return;
+    const int threads = 256;
+    long long total = rows * (ld >> 1);
+    long long blocks = (total + threads - 1) / threads;
+    long long cap = (long long)sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    log_returns_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, out, rows, n_assets, ld);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-per-row column accumulation over rows [r0, r0+nr) of a row-major matrix with leading
+// dimension ld, restricted to the 512-column block starting at col0.  Lane l owns columns
+// col0 + 64*ch + 2*l (+1), ch = 0..7, so every row is read with coalesced 16-byte loads.
+//   sum[ch]  += x            wsum[ch] += wgt[k] * x            (wgt may be null)
+//   if DOT:  y[k] (+)= sum_c x_c * w0[c]   (row dot with a shared-memory vector)
+constexpr int PREP_THREADS = 256;
+constexpr int PREP_WARPS = PREP_THREADS / 32;
+constexpr int NCH = 8;
+
+template <bool DOT>
+__device__ __forceinline__ void col_accumulate(const double* __restrict__ M, int ld, long long r0, int nr,
+                                               int col0, const double* wgt, const double* w0s, double* y,
+                                               bool y_accumulate, double2 (&sum)[NCH], double2 (&wsum)[NCH]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        sum[ch] = make_double2(0.0, 0.0);
+        wsum[ch] = make_double2(0.0, 0.0);
+    }
+    for (int k = warp; k < nr; k += PREP_WARPS) {
+        const double* row = M + (r0 + k) * (long long)ld + col0;
+        const double wk = wgt ? wgt[k] : 0.0;
+        double dot = 0.0;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int c = ch * 64 + lane * 2;
+            if (col0 + c < ld) {
+                const double2 x = *reinterpret_cast<const double2*>(row + c);
+                sum[ch].x += x.x;
+                sum[ch].y += x.y;
+                wsum[ch].x = fma(wk, x.x, wsum[ch].x);
+                wsum[ch].y = fma(wk, x.y, wsum[ch].y);
+                if (DOT) dot = fma(x.x, w0s[col0 + c], fma(x.y, w0s[col0 + c + 1], dot));
+            }
+        }
+        if (DOT) {
+            dot = warp_sum(dot);
+            if (lane == 0) y[k] = y_accumulate ? y[k] + dot : dot;
+        }
+    }
+}
+
+// Cross-warp reduction of the per-lane column partials through shared memory `red`
+// ([PREP_WARPS][512] doubles); thread j of the block ends up owning columns col0+2j, col0+2j+1.
+__device__ __forceinline__ double2 reduce_cols(const double2 (&part)[NCH], double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+        *reinterpret_cast<double2*>(red + warp * 512 + ch * 64 + lane * 2) = part[ch];
+    __syncthreads();
+    double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int wv = 0; wv < PREP_WARPS; ++wv) {
+        const double2 v = *reinterpret_cast<const double2*>(red + wv * 512 + threadIdx.x * 2);
+        s.x += v.x;
+        s.y += v.y;
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(PREP_THREADS) window_prep_kernel(PrepParams p) {
+    extern __shared__ double smem[];
+    const int K = p.n_window - 1;                 // daily returns per window (F2)
+    double* a_s = smem;                           // [K]
+    double* w0_s = a_s + ((K + 1) & ~1);          // [ldv]
+    double* red = w0_s + p.ldv;                   // [PREP_WARPS][512]
+    double* scratch = red + PREP_WARPS * 512;     // [40]
+
+    const int w = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int N = p.n_assets;
+    const int day_row = p.day_row[w];
+    const long long r0 = (long long)day_row - K + 1;   // first return row of the window
+    double* scal = p.scal + (long long)w * BP_S_COUNT;
+
+    // ---- a_k = (1 + rf)^(gbar/365) - 1  (:40-48); gbar = calendar span / (n-1)
+    const double gbar = (double)p.span_days[w] / (double)K;
+    const double expo = gbar / 365.0;
+    double sa = 0.0, saa = 0.0;
+    for (int k = tid; k < K; k += PREP_THREADS) {
+        const double a = pow(1.0 + p.rf_row[r0 + k], expo) - 1.0;
+        a_s[k] = a;
+        sa += a;
+        saa = fma(a, a, saa);
+    }
+    sa = block_sum(sa, scratch);
+    saa = block_sum(saa, scratch);
+
+    double2 sum[NCH], wsum[NCH];
+    // ---- daily column sums: t = L'1 - (sum a),  p = L'a - (a'a)/2
+    for (int col0 = 0; col0 < p.ldv; col0 += 512) {
+        col_accumulate<false>(p.lr_daily, p.ld, r0, K, col0, a_s, nullptr, nullptr, false, sum, wsum);
+        const double2 ts = reduce_cols(sum, red);
+        const double2 us = reduce_cols(wsum, red);
+        const int c = col0 + tid * 2;
+        if (c < p.ldv) {
+            double2 tv = make_double2(c < N ? ts.x - sa : 0.0, c + 1 < N ? ts.y - sa : 0.0);
+            double2 pv = make_double2(c < N ? us.x - 0.5 * saa : 0.0, c + 1 < N ? us.y - 0.5 * saa : 0.0);
+            *reinterpret_cast<double2*>(p.t + (long long)w * p.ldv + c) = tv;
+            *reinterpret_cast<double2*>(p.pvec + (long long)w * p.ldv + c) = pv;
+            if (p.mode == BP_MODE_JEFFREYS) {
+                *reinterpret_cast<double2*>(p.gvec + (long long)w * p.ldv + c) = tv;
+                *reinterpret_cast<double2*>(p.rhs + (long long)w * p.ldv + c) = tv;
+            }
+        }
+    }
+    if (p.mode == BP_MODE_JEFFREYS) {
+        if (tid == 0) {
+            scal[BP_S_N0] = 0.0;
+            scal[BP_S_N1] = 0.0;
+            scal[BP_S_ALPHA] = 0.0;
+            scal[BP_S_BETA] = 1.0 / (double)p.n_window;     // J = T - (1/n) t t'  (:600)
+            scal[BP_S_C] = 0.0;
+            scal[BP_S_V0] = 0.0;
+            scal[BP_S_M] = 0.0;
+            scal[BP_S_SUMA] = sa;
+        }
+        return;
+    }
+
+    // ---- MCM scaling (:90-114, :247-282): mean of the last n observations incl. d
+    const double* mcm = p.mcm;
+    double ms = 0.0;
+    for (int k = tid; k < p.n_window; k += PREP_THREADS) ms += mcm[day_row - p.n_window + 1 + k];
+    ms = block_sum(ms, scratch);
+    const double avg = ms / (double)p.n_window;
+    const double cur = mcm[day_row];
+    const double frac = cur > avg ? cur / avg : avg / cur;
+    const double n0 = (double)p.n_window * frac * p.mcm_scaling;
+    const double n1 = n0 + (double)p.n_window;
+
+    // ---- prior weights w0 (:679-701 value weighted, :661-677 equally weighted)
+    double cs = 0.0;
+    if (p.prior_kind == BP_PRIOR_VW) {
+        for (int j = tid; j < N; j += PREP_THREADS) cs += p.caps[(long long)day_row * p.ld + j];
+        cs = block_sum(cs, scratch);
+    }
+    for (int j = tid; j < p.ldv; j += PREP_THREADS) {
+        double v = 0.0;
+        if (j < N) v = p.prior_kind == BP_PRIOR_VW ? p.caps[(long long)day_row * p.ld + j] / cs : 1.0 / (double)N;
+        w0_s[j] = v;
+        p.w0[(long long)w * p.ldv + j] = v;
+    }
+    __syncthreads();
+
+    // ---- HF pass 1: column means hbar and row dots y_k = h_k . w0   (:314-318)
+    const long long h0 = (long long)p.hf_row0[w];           // first HF return row (first bar dropped, F5)
+    const int m = p.hf_m[w];                                // HF returns in the window
+    double* y = p.y_ws + (long long)w * p.y_stride;
+    for (int col0 = 0; col0 < p.ldv; col0 += 512) {
+        col_accumulate<true>(p.lr_hf, p.ld, h0, m, col0, nullptr, w0_s, y, col0 > 0, sum, wsum);
+        const double2 hs = reduce_cols(sum, red);
+        const int c = col0 + tid * 2;
+        if (c < p.ldv) {
+            double2 hb = make_double2(c < N ? hs.x / (double)m : 0.0, c + 1 < N ? hs.y / (double)m : 0.0);
+            *reinterpret_cast<double2*>(p.gvec + (long long)w * p.ldv + c) = hb;
+        }
+    }
+    __syncthreads();
+    // centre y:  y_c = y - mean(y)   (sum_k y_c = 0 => S0 w0 = alpha * H' y_c, v0 = alpha * |y_c|^2)
+    double ys = 0.0;
+    for (int k = tid; k < m; k += PREP_THREADS) ys += y[k];
+    ys = block_sum(ys, scratch);
+    const double ybar = ys / (double)m;
+    double yy = 0.0;
+    for (int k = tid; k < m; k += PREP_THREADS) {
+        const double v = y[k] - ybar;
+        y[k] = v;
+        yy = fma(v, v, yy);
+    }
+    yy = block_sum(yy, scratch);      // block_sum's barriers also publish the centred y to the block
+
+    const double alpha = n0 * ((double)m / (double)(m - 1));   // S0 = n0 * cov * m  (:317-318, :333)
+    const double v0 = alpha * yy;
+    const double kk = n0 + (double)N + 2.0;
+    const double cc = (2.0 * n0) / (kk + sqrt(kk * kk + 4.0 * n0 * v0));   // :415-418
+
+    // ---- HF pass 2: q = H' y_c ;  b = c * S0 w0 + t   (:489)
+    for (int col0 = 0; col0 < p.ldv; col0 += 512) {
+        col_accumulate<false>(p.lr_hf, p.ld, h0, m, col0, y, nullptr, nullptr, false, sum, wsum);
+        const double2 qs = reduce_cols(wsum, red);
+        const int c = col0 + tid * 2;
+        if (c < p.ldv) {
+            const double2 tv = *reinterpret_cast<const double2*>(p.t + (long long)w * p.ldv + c);
+            double2 s0w0 = make_double2(c < N ? alpha * qs.x : 0.0, c + 1 < N ? alpha * qs.y : 0.0);
+            double2 bv = make_double2(c < N ? fma(cc, s0w0.x, tv.x) : 0.0, c + 1 < N ? fma(cc, s0w0.y, tv.y) : 0.0);
+            *reinterpret_cast<double2*>(p.s0w0 + (long long)w * p.ldv + c) = s0w0;
+            *reinterpret_cast<double2*>(p.rhs + (long long)w * p.ldv + c) = bv;
+        }
+    }
+    if (tid == 0) {
+        scal[BP_S_N0] = n0;
+        scal[BP_S_N1] = n1;
+        scal[BP_S_ALPHA] = alpha;
+        scal[BP_S_BETA] = alpha * (double)m;     // S0 = alpha * (H'H - m hbar hbar')
+        scal[BP_S_C] = cc;
+        scal[BP_S_V0] = v0;
+        scal[BP_S_M] = (double)m;
+        scal[BP_S_SUMA] = sa;
+    }
+}
+
+size_t prep_smem_bytes(int n_window, int ldv) {
+    const int K = n_window - 1;
+    return sizeof(double) * (size_t)(((K + 1) & ~1) + ldv + PREP_WARPS * 512 + 40);
+}
+
+cudaError_t launch_window_prep(const PrepParams& p, int n_windows, cudaStream_t st) {
+    if (n_windows <= 0) return cudaSuccess;
+    const size_t smem = prep_smem_bytes(p.n_window, p.ldv);
+    cudaError_t e = cudaFuncSetAttribute(window_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    window_prep_kernel<<<n_windows, PREP_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Padded lower-triangular device layout [rowsS][ldS]  ->  dense symmetric [N][N]
+__global__ void unpack_sym_kernel(const double* __restrict__ S, long long win_stride, int ldS, int N,
+                                  double* __restrict__ out) {
+    const int w = blockIdx.y;
+    const double* s = S + (long long)w * win_stride;
+    double* o = out + (long long)w * N * N;
+    const long long total = (long long)N * N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int r = int(i / N), c = int(i - (long long)r * N);
+        o[i] = r >= c ? s[(long long)r * ldS + c] : s[(long long)c * ldS + r];
+    }
+}
+
+void launch_unpack_sym(const double* S, long long win_stride, int ldS, int N, int W, double* out, cudaStream_t st) {
+    if (W <= 0) return;
+    long long total = (long long)N * N;
+    int bx = (int)((total + 255) / 256);
+    if (bx > 256) bx = 256;
+    dim3 grid(bx, W);
+    unpack_sym_kernel<<<grid, 256, 0, st>>>(S, win_stride, ldS, N, out);
+}
+
+// Strided [W][ldv] vectors -> dense [W][N]
+__global__ void unpack_vec_kernel(const double* __restrict__ v, int ldv, int N, long long W, double* __restrict__ out) {
+    const long long total = W * N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long w = i / N;
+        const int c = int(i - w * N);
+        out[i] = v[w * ldv + c];
+    }
+}
+
+void launch_unpack_vec(const double* v, int ldv, int N, long long W, double* out, cudaStream_t st) {
+    if (W <= 0) return;
+    long long total = W * N;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    unpack_vec_kernel<<<(unsigned)blocks, 256, 0, st>>>(v, ldv, N, W, out);
+}
+
+}  // namespace bp

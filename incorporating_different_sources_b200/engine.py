@@ -1,0 +1,286 @@
+"""Batched Bayesian tangency-weight engine: the host side above the C-ABI.
+
+``BayesEngine`` keeps one market resident in HBM and evaluates *all* rebalance windows of a
+backtest per call (the reference evaluates one window per Python call,
+``portfolio_calculations.py:1232-1234``).  PyTorch is used only as plumbing: device output
+buffers, the CUDA stream, and (in ``sharding.py``) ``torch.distributed``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import BP_NSCAL, SCAL, MarketDesc, Outputs, WindowBatchDesc
+from .windows import WindowBatch
+
+VEC_OUTPUTS = ("weights", "nu", "w1", "t", "w0", "rhs")
+MAT_OUTPUTS = ("T", "S0", "S1")
+ALL_OUTPUTS = VEC_OUTPUTS + MAT_OUTPUTS + ("scalars", "status")
+
+
+class BayesPortfolioError(RuntimeError):
+    pass
+
+
+def _raise(rc: int):
+    msg = _lib.last_error()
+    if rc == _lib.BP_ERR_INVALID:
+        raise ValueError(msg)
+    raise BayesPortfolioError(f"libbayes_portfolio error {rc}: {msg}")
+
+
+def _c64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class BayesEngine:
+    """One CUDA device, one resident market.
+
+    Parameters
+    ----------
+    device : CUDA device ordinal.
+    use_torch_stream : launch on torch's current stream so that ``torch.cuda.Event`` timing and
+        ``torch.distributed`` collectives order correctly with the kernels.
+    """
+
+    def __init__(self, device: int = 0, use_torch_stream: bool = True):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.bp_init(int(device), C.byref(h))
+        if rc != 0:
+            _raise(rc)
+        self._h = h
+        self.device = int(device)
+        self.n_assets = 0
+        self.n_days = 0
+        self.n_hf_rows = 0
+        self._torch = None
+        if use_torch_stream:
+            import torch
+            self._torch = torch
+            torch.cuda.set_device(self.device)
+            self.bind_torch_stream()
+
+    # ------------------------------------------------------------------ plumbing
+    def bind_torch_stream(self):
+        torch = self._torch
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self._lib.bp_set_stream(self._h, C.c_void_p(stream))
+        if rc:
+            _raise(rc)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.bp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        rc = self._lib.bp_synchronize(self._h)
+        if rc:
+            _raise(rc)
+
+    def set_workspace_limit(self, nbytes: int):
+        rc = self._lib.bp_set_workspace_limit(self._h, C.c_size_t(int(nbytes)))
+        if rc:
+            _raise(rc)
+
+    def device_info(self) -> Dict[str, int]:
+        sm = C.c_int()
+        fr = C.c_size_t()
+        tot = C.c_size_t()
+        rc = self._lib.bp_device_info(self._h, C.byref(sm), C.byref(fr), C.byref(tot))
+        if rc:
+            _raise(rc)
+        return {"sm_count": sm.value, "free_bytes": fr.value, "total_bytes": tot.value}
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.bp_launch_count(self._h))
+
+    # ------------------------------------------------------------------ market
+    def upload_market(self, prices, rf_row, caps=None, hf_prices=None, mcm=None):
+        """Host arrays -> HBM.  ``prices`` [D][N], ``rf_row`` [D] (risk-free rate forward-filled onto
+        the daily rows), ``caps`` [D][N], ``hf_prices`` [R][N], ``mcm`` [n_mcm][D] (row 0 VIX, row 1 EPU)."""
+        prices = _c64(prices)
+        rf_row = _c64(rf_row)
+        D, N = prices.shape
+        if rf_row.shape != (D,):
+            raise ValueError("rf_row must have one entry per daily row")
+        if np.isnan(rf_row).any():
+            raise ValueError("risk-free rate undefined on some window dates (the reference would drop rows, :60)")
+        keep = [prices, rf_row]
+        desc = MarketDesc()
+        desc.n_assets, desc.n_days = N, D
+        desc.prices = prices.ctypes.data
+        desc.rf_row = rf_row.ctypes.data
+        desc.caps = None
+        desc.hf_prices = None
+        desc.n_hf_rows = 0
+        desc.mcm = None
+        desc.n_mcm = 0
+        if caps is not None:
+            caps = _c64(caps)
+            if caps.shape != (D, N):
+                raise ValueError("caps must match prices")
+            keep.append(caps)
+            desc.caps = caps.ctypes.data
+        if hf_prices is not None and len(hf_prices):
+            hf_prices = _c64(hf_prices)
+            if hf_prices.shape[1] != N:
+                raise ValueError("hf_prices must have N columns")
+            keep.append(hf_prices)
+            desc.hf_prices = hf_prices.ctypes.data
+            desc.n_hf_rows = hf_prices.shape[0]
+        if mcm is not None:
+            mcm = _c64(mcm)
+            if mcm.ndim == 1:
+                mcm = mcm[None, :]
+            if mcm.shape[1] != D:
+                raise ValueError("mcm series must be aligned with the daily rows")
+            keep.append(mcm)
+            desc.mcm = mcm.ctypes.data
+            desc.n_mcm = mcm.shape[0]
+        rc = self._lib.bp_upload_market(self._h, C.byref(desc))
+        if rc:
+            _raise(rc)
+        self.n_assets, self.n_days, self.n_hf_rows = N, D, int(desc.n_hf_rows)
+        del keep
+
+    def prepare_market(self):
+        """Re-run the on-device log-return stage (used to time the whole device path)."""
+        rc = self._lib.bp_prepare_market(self._h)
+        if rc:
+            _raise(rc)
+
+    # ------------------------------------------------------------------ batches
+    def _batch_desc(self, b: WindowBatch, need_hf: bool):
+        keep = []
+        d = WindowBatchDesc()
+        d.n_windows = b.n_windows
+        d.rolling_window = int(b.rolling_window)
+        for name in ("day_row", "span_days"):
+            a = np.ascontiguousarray(getattr(b, name), dtype=np.int32)
+            keep.append(a)
+            setattr(d, name, a.ctypes.data)
+        d.hf_lo = None
+        d.hf_hi = None
+        if need_hf:
+            if b.hf_lo is None or b.hf_hi is None:
+                raise ValueError("this batch has no intraday window rows")
+            for name in ("hf_lo", "hf_hi"):
+                a = np.ascontiguousarray(getattr(b, name), dtype=np.int32)
+                keep.append(a)
+                setattr(d, name, a.ctypes.data)
+        d.mcm_index = int(b.mcm_index)
+        d.mcm_scaling = float(b.mcm_scaling)
+        d.risk_aversion = float(b.risk_aversion)
+        d.prior_weights = int(b.prior_weights)
+        return d, keep
+
+    def _alloc_outputs(self, W: int, names: Iterable[str], device_out: bool, into: Optional[dict]):
+        N = self.n_assets
+        o = Outputs()
+        res = {}
+        for f, _ in Outputs._fields_:
+            setattr(o, f, None)
+        for name in names:
+            if name not in ALL_OUTPUTS:
+                raise KeyError(name)
+            if name in VEC_OUTPUTS:
+                shape, dt = (W, N), np.float64
+            elif name in MAT_OUTPUTS:
+                shape, dt = (W, N, N), np.float64
+            elif name == "scalars":
+                shape, dt = (W, BP_NSCAL), np.float64
+            else:
+                shape, dt = (W,), np.int32
+            if into is not None and name in into:
+                buf = into[name]
+            elif device_out:
+                torch = self._torch
+                buf = torch.empty(shape, dtype=torch.float64 if dt is np.float64 else torch.int32,
+                                  device=f"cuda:{self.device}")
+            else:
+                buf = np.empty(shape, dtype=dt)
+            res[name] = buf
+            ptr = buf.data_ptr() if hasattr(buf, "data_ptr") else buf.ctypes.data
+            setattr(o, name, ptr)
+        return o, res
+
+    def _run(self, fn, b: WindowBatch, outputs, device_out, into, need_hf):
+        d, keep = self._batch_desc(b, need_hf)
+        o, res = self._alloc_outputs(b.n_windows, outputs, device_out, into)
+        rc = fn(self._h, C.byref(d), C.byref(o))
+        del keep
+        if rc:
+            _raise(rc)
+        return res
+
+    def conjugate(self, batch: WindowBatch, outputs: Sequence[str] = ("weights", "status"),
+                  device_out: bool = False, into: Optional[dict] = None) -> Dict[str, object]:
+        """``calculate_conjugate_hf_mcm_portfolio`` (:819-836) for every window of the batch."""
+        return self._run(self._lib.bp_conjugate_batched, batch, outputs, device_out, into, True)
+
+    def jeffreys(self, batch: WindowBatch, outputs: Sequence[str] = ("weights", "status"),
+                 device_out: bool = False, into: Optional[dict] = None) -> Dict[str, object]:
+        """``calculate_jeffreys_portfolio`` (:838-849) for every window of the batch."""
+        return self._run(self._lib.bp_jeffreys_batched, batch, outputs, device_out, into, False)
+
+    def stats(self, batch: WindowBatch, want_T: bool = True):
+        """``calculate_canonical_statistics_t`` / ``_T`` (:163-245)."""
+        d, keep = self._batch_desc(batch, False)
+        W, N = batch.n_windows, self.n_assets
+        t = np.empty((W, N))
+        T = np.empty((W, N, N)) if want_T else None
+        rc = self._lib.bp_stats_batched(self._h, C.byref(d), t.ctypes.data, T.ctypes.data if want_T else None)
+        del keep
+        if rc:
+            _raise(rc)
+        return t, T
+
+    def hf_cov(self, batch: WindowBatch):
+        """``calculate_conjugate_prior_n`` / ``_S`` (:247-267, :285-333): (n0 [W], S0 [W][N][N])."""
+        d, keep = self._batch_desc(batch, True)
+        W, N = batch.n_windows, self.n_assets
+        n0 = np.empty(W)
+        S0 = np.empty((W, N, N))
+        rc = self._lib.bp_hf_cov_batched(self._h, C.byref(d), n0.ctypes.data, S0.ctypes.data)
+        del keep
+        if rc:
+            _raise(rc)
+        return n0, S0
+
+
+def scalars_to_dict(scal_row: np.ndarray) -> Dict[str, float]:
+    return {k: float(scal_row[i]) for k, i in SCAL.items()}
+
+
+def upload_synthetic(engine: BayesEngine, mkt, cols=None, day_slice: Optional[slice] = None):
+    """Upload a :class:`SyntheticMarket` (optionally a column subset / contiguous day range).
+
+    Returns (row_offset, hf_row_offset): what to subtract from market row numbers to obtain rows of
+    the resident slice.
+    """
+    from .windows import ffill_rows
+    cols = np.arange(mkt.n_assets) if cols is None else np.asarray(cols)
+    ds = day_slice or slice(0, mkt.n_days)
+    d0, d1 = ds.start or 0, ds.stop if ds.stop is not None else mkt.n_days
+    bars = len(mkt.hf_ts) // mkt.n_days
+    h0, h1 = d0 * bars, d1 * bars
+    full = cols.shape[0] == mkt.n_assets and np.array_equal(cols, np.arange(mkt.n_assets))
+    pick = (lambda a: a) if full else (lambda a: a[:, cols])
+    rf_dates = getattr(mkt, "rf_dates", mkt.dates)
+    rf_row = ffill_rows(mkt.dates[d0:d1], rf_dates, mkt.rf)
+    engine.upload_market(
+        prices=pick(mkt.prices[d0:d1]), rf_row=rf_row, caps=pick(mkt.caps[d0:d1]),
+        hf_prices=pick(mkt.hf_prices[h0:h1]), mcm=np.stack([mkt.vix[d0:d1], mkt.epu[d0:d1]]))
+    return d0, h0

@@ -1,0 +1,122 @@
+"""Host-side integer work of the path: which rows make up each rebalance window.
+
+Everything here is index arithmetic on dates and must be bit-exact with the reference
+(SURVEY.md H6): ``rolling_window`` counts PRICES so a window has n-1 returns (F2,
+``portfolio_calculations.py:159,:60``); the risk-free exponent uses the window's own calendar
+span (F3, ``:40-41``); the intraday window is ``(d - D + 1 day, d + 1 day]`` with the first bar's
+return dropped (F5, ``:310-314``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+_DAY = np.timedelta64(1, "D")
+HF_LOOKBACK_DAYS = {"daily": 1, "weekly": 7, "monthly": 31}     # portfolio_calculations.py:299-304
+
+
+@dataclass
+class WindowBatch:
+    """One batch of rebalance windows sharing a ``portfolio_spec`` (mirrors ``bp_window_batch``)."""
+    rolling_window: int
+    day_row: np.ndarray          # int32 [W] row of the trade date in the uploaded daily arrays
+    span_days: np.ndarray        # int32 [W] calendar days first -> last window date
+    hf_lo: Optional[np.ndarray]  # int32 [W] intraday price rows [lo, hi)
+    hf_hi: Optional[np.ndarray]
+    mcm_index: int = 0
+    mcm_scaling: float = 1.0
+    risk_aversion: float = 1.0
+    prior_weights: int = 0       # 0 value weighted, 1 equally weighted
+
+    @property
+    def n_windows(self) -> int:
+        return int(self.day_row.shape[0])
+
+
+def mcm_index_of(strategy: str) -> int:
+    """Column of the uploaded MCM block: 0 = VIX, 1 = EPU (dispatcher at :1012-1028)."""
+    if "vix" in strategy:
+        return 0
+    if "epu" in strategy:
+        return 1
+    return 0
+
+
+def prior_kind_of(strategy: str) -> int:
+    """``calculate_conjugate_prior_w`` (:369-378): 'vw' is tested before 'ew'."""
+    if "vw" in strategy:
+        return 0
+    if "ew" in strategy:
+        return 1
+    raise ValueError("Unknown conjugate portfolio prior weights.")
+
+
+def hf_lookback(spec, hf_lookback_days: Optional[int] = None) -> int:
+    if hf_lookback_days is not None:
+        return int(hf_lookback_days)
+    freq = spec["rolling_window_frequency"]
+    if freq not in HF_LOOKBACK_DAYS:
+        raise RuntimeError("Unknown rolling window frequency.")               # :308
+    return HF_LOOKBACK_DAYS[freq]
+
+
+def plan_daily_windows(spec, dates: np.ndarray, d_indices: Sequence[int], hf_ts: Optional[np.ndarray] = None,
+                       hf_lookback_days: Optional[int] = None, need_hf: bool = True,
+                       row_offset: int = 0, hf_row_offset: int = 0) -> WindowBatch:
+    """Window descriptors for ``rolling_window_frequency == 'daily'``.
+
+    ``dates`` is the (sorted) business-day index of the uploaded daily arrays, ``d_indices`` the
+    positions of the trade dates in it.  ``row_offset`` / ``hf_row_offset`` shift the produced row
+    numbers when only a slice of the market (a rank's date shard plus halo) is resident.
+    """
+    n = int(spec["rolling_window"])
+    d_idx = np.asarray(d_indices, dtype=np.int64)
+    if d_idx.ndim != 1 or d_idx.size == 0:
+        raise ValueError("need at least one trade date")
+    if d_idx.min() < n - 1:
+        raise ValueError(f"a window of {n} prices needs {n - 1} rows before the trade date")
+    first = d_idx - (n - 1)
+    days = dates.astype("datetime64[D]").astype(np.int64)
+    span = days[d_idx] - days[first]
+    # the reference asserts max gap <= mean gap + 4 inside every window (:40-44)
+    gaps = np.diff(days)
+    win_gaps = np.lib.stride_tricks.sliding_window_view(gaps, n - 1)[first]
+    assert np.all(win_gaps.max(axis=1) <= span / (n - 1) + 4), "Unexpected large gap between return dates."
+    hf_lo = hf_hi = None
+    if need_hf:
+        if hf_ts is None:
+            raise ValueError("intraday timestamps required for the conjugate prior")
+        D = hf_lookback(spec, hf_lookback_days)
+        d = dates[d_idx]
+        start = d - D * _DAY + _DAY                                              # :310-311
+        hf_lo = np.searchsorted(hf_ts, start, side="right")
+        hf_hi = np.searchsorted(hf_ts, d + _DAY, side="right")                   # :312
+        hf_lo = (hf_lo - hf_row_offset).astype(np.int32)
+        hf_hi = (hf_hi - hf_row_offset).astype(np.int32)
+    strat = spec["weighting_strategy"]
+    conj = strat.startswith("conjugate")
+    return WindowBatch(
+        rolling_window=n,
+        day_row=(d_idx - row_offset).astype(np.int32),
+        span_days=span.astype(np.int32),
+        hf_lo=hf_lo, hf_hi=hf_hi,
+        mcm_index=mcm_index_of(strat) if conj else 0,
+        mcm_scaling=float(spec["mcm_scaling"]) if conj and spec.get("mcm_scaling") is not None else 1.0,
+        risk_aversion=float(spec["risk_aversion"]) if spec.get("risk_aversion") is not None else 1.0,
+        prior_weights=prior_kind_of(strat) if conj else 0,
+    )
+
+
+def ffill_rows(target_dates: np.ndarray, src_dates: np.ndarray, src_values: np.ndarray) -> np.ndarray:
+    """``series.reindex(target, method='ffill')`` (:54) for sorted date arrays."""
+    idx = np.searchsorted(src_dates, target_dates, side="right") - 1
+    out = np.where(idx >= 0, src_values[np.maximum(idx, 0)], np.nan)
+    return out.astype(np.float64)
+
+
+def cap_descending_order(caps_row: np.ndarray, size: int, eligible: Optional[np.ndarray] = None) -> np.ndarray:
+    """Asset set and order of one window: ``nlargest(size)`` of the caps at d (:653-654, F7)."""
+    cand = np.arange(caps_row.shape[0]) if eligible is None else np.asarray(eligible)
+    return cand[np.argsort(-caps_row[cand], kind="stable")][:size]

@@ -1,0 +1,137 @@
+"""CUDA path (through the C-ABI) against the reference-generated golden vectors and the oracle.
+
+Tolerance (BASELINE.json north_star): weights and posterior moments within 1e-9 relative in FP64,
+measured as max|x_gpu - x_ref| / max|x_ref|; window and asset indexing bit-exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import bayes_oracle as bo
+from tests._golden import check_matrix, golden_names, load_golden, market_for, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+DAILY = [n for n in golden_names()]
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from incorporating_different_sources_b200.engine import BayesEngine
+    eng = BayesEngine(0)
+    yield eng
+    eng.close()
+
+
+def _daily(meta):
+    return meta["spec"]["rolling_window_frequency"] == "daily"
+
+
+@pytest.mark.parametrize("name", DAILY)
+def test_gpu_matches_reference_golden(engine, name):
+    from incorporating_different_sources_b200.engine import upload_synthetic
+    from incorporating_different_sources_b200.windows import plan_daily_windows
+    z, meta = load_golden(name)
+    if not _daily(meta):
+        pytest.skip("weekly windows are covered by test_gpu_weekly.py")
+    mkt = market_for(meta)
+    spec = meta["spec"]
+    conj = spec["weighting_strategy"].startswith("conjugate")
+    for wi, w in enumerate(meta["windows"]):
+        pre = f"w{wi}_"
+        d_idx = w["d_idx"]
+        cols = z[pre + "cols"]
+        upload_synthetic(engine, mkt, cols=cols)
+        batch = plan_daily_windows(spec, mkt.dates, [d_idx], mkt.hf_ts, hf_lookback_days=meta["hf_days"],
+                                   need_hf=conj)
+        if conj:
+            got = engine.conjugate(batch, outputs=("weights", "nu", "w1", "t", "w0", "scalars", "status", "T", "S0", "S1"))
+            assert got["status"][0] == 0
+            s = got["scalars"][0]
+            for k, i in (("n0", 0), ("n1", 1), ("c", 4), ("v1", 8)):
+                assert abs(s[i] - float(z[pre + k])) <= TOL * abs(float(z[pre + k])), k
+            for k in ("t", "w0", "w1", "nu", "weights"):
+                assert relerr(got[k][0], z[pre + k]) <= TOL, k
+            for k in ("T", "S0", "S1"):
+                check_matrix(k, got[k][0], z, pre, TOL)
+        else:
+            got = engine.jeffreys(batch, outputs=("weights", "nu", "t", "status", "T"))
+            assert got["status"][0] == 0
+            for k in ("t", "nu", "weights"):
+                assert relerr(got[k][0], z[pre + k]) <= TOL, k
+            check_matrix("T", got["T"][0], z, pre, TOL)
+
+
+@pytest.mark.parametrize("n_assets,hf_days,n_windows", [(10, None, 40), (50, 7, 25), (130, 7, 12), (100, 31, 6)])
+def test_gpu_batched_matches_oracle(engine, n_assets, hf_days, n_windows):
+    """Many overlapping windows in one call vs the oracle evaluated window by window."""
+    from incorporating_different_sources_b200.engine import upload_synthetic
+    from incorporating_different_sources_b200.synthetic import generate_market
+    from incorporating_different_sources_b200.windows import plan_daily_windows
+    mkt = generate_market(n_assets, 300, seed=4000 + n_assets)
+    spec = dict(weighting_strategy="conjugate_hf_epu_vw", size=n_assets, risk_aversion=4, turnover_cost=15,
+                rebalancing_frequency="daily", rolling_window=252, rolling_window_frequency="daily",
+                mcm_scaling=2, display_name="x")
+    d_idx = list(range(300 - n_windows, 300))
+    cols = np.arange(n_assets)
+    upload_synthetic(engine, mkt)
+    batch = plan_daily_windows(spec, mkt.dates, d_idx, mkt.hf_ts, hf_lookback_days=hf_days)
+    got = engine.conjugate(batch, outputs=("weights", "w1", "scalars", "status"))
+    jspec = dict(spec, weighting_strategy="jeffreys")
+    jb = plan_daily_windows(jspec, mkt.dates, d_idx, need_hf=False)
+    gotj = engine.jeffreys(jb, outputs=("weights", "status"))
+    assert not got["status"].any() and not gotj["status"].any()
+    for i, d in enumerate(d_idx):
+        ref = bo.conjugate_window(spec, mkt, d, cols, hf_lookback_days=hf_days)
+        assert relerr(got["weights"][i], ref["weights"]) <= TOL
+        assert relerr(got["w1"][i], ref["w1"]) <= TOL
+        assert abs(got["scalars"][i][4] - ref["c"]) <= TOL * abs(ref["c"])
+        refj = bo.jeffreys_window(jspec, mkt, d, cols)
+        assert relerr(gotj["weights"][i], refj["weights"]) <= TOL
+
+
+def test_gpu_stats_and_hf_cov_entry_points(engine):
+    from incorporating_different_sources_b200.engine import upload_synthetic
+    from incorporating_different_sources_b200.synthetic import generate_market
+    from incorporating_different_sources_b200.windows import plan_daily_windows
+    mkt = generate_market(37, 280, seed=77)        # odd N: exercises every padding path
+    spec = dict(weighting_strategy="conjugate_hf_vix_ew", size=37, risk_aversion=5, rolling_window=252,
+                rolling_window_frequency="daily", mcm_scaling=1)
+    d_idx = [270, 279]
+    upload_synthetic(engine, mkt)
+    batch = plan_daily_windows(spec, mkt.dates, d_idx, mkt.hf_ts)
+    t, T = engine.stats(batch)
+    n0, S0 = engine.hf_cov(batch)
+    cols = np.arange(37)
+    for i, d in enumerate(d_idx):
+        ref = bo.conjugate_window(spec, mkt, d, cols)
+        assert relerr(t[i], ref["t"]) <= TOL and relerr(T[i], ref["T"]) <= TOL
+        assert abs(n0[i] - ref["n0"]) <= TOL * ref["n0"] and relerr(S0[i], ref["S0"]) <= TOL
+        assert np.array_equal(T[i], T[i].T)
+
+
+def test_gpu_status_flags_singular_window(engine):
+    """N >= n-1 with a 1-day HF prior is singular in the reference: the CUDA path must
+    flag the window instead of returning silent garbage."""
+    from incorporating_different_sources_b200.engine import upload_synthetic
+    from incorporating_different_sources_b200.synthetic import generate_market
+    from incorporating_different_sources_b200.windows import plan_daily_windows
+    mkt = generate_market(64, 70, seed=5)
+    spec = dict(weighting_strategy="jeffreys", size=64, risk_aversion=5, rolling_window=40,
+                rolling_window_frequency="daily", mcm_scaling=None)
+    upload_synthetic(engine, mkt)
+    jb = plan_daily_windows(spec, mkt.dates, [69], need_hf=False)
+    got = engine.jeffreys(jb, outputs=("weights", "status"))
+    assert got["status"][0] != 0
+
+
+def test_gpu_invalid_arguments_raise(engine):
+    from incorporating_different_sources_b200.engine import upload_synthetic
+    from incorporating_different_sources_b200.synthetic import generate_market
+    from incorporating_different_sources_b200.windows import WindowBatch
+    mkt = generate_market(8, 60, seed=5)
+    upload_synthetic(engine, mkt)
+    bad = WindowBatch(rolling_window=252, day_row=np.array([59], dtype=np.int32),
+                      span_days=np.array([350], dtype=np.int32), hf_lo=None, hf_hi=None)
+    with pytest.raises(ValueError):
+        engine.jeffreys(bad)
