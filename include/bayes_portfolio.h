@@ -44,6 +44,13 @@ extern "C" {
 #define BP_SCAL_SUMA 7        /* sum of risk-free adjustments  :48                                   */
 #define BP_SCAL_V1 8          /* w1' S1 w1                     :574                                  */
 
+/* stages reported by bp_get_stage_times */
+#define BP_NSTAGE 8
+#define BP_STAGE_LOGRET 0     /* prices -> log returns                  :37, :314                    */
+#define BP_STAGE_PREP 1       /* per-window O(N K) reductions + scalars :40-57,:90-114,:247-282,:361-430 */
+#define BP_STAGE_GRAM 2       /* batched Gram / covariance (DMMA)       :180-182, :317-318, :358, :600 */
+#define BP_STAGE_SOLVE 3      /* Cholesky + solves + weights            :485-489, :572-575, :602-606  */
+
 typedef struct bp_handle bp_handle;
 
 /* The data the weight functions read (the frames of data_handling.py:282-291, already aligned to
@@ -105,6 +112,11 @@ int bp_set_workspace_limit(bp_handle* h, size_t bytes);
 int bp_device_info(bp_handle* h, int* sm_count, size_t* free_bytes, size_t* total_bytes);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 long long bp_launch_count(bp_handle* h);
+
+/* Per-stage device timing with CUDA events on the handle's stream.  bp_get_stage_times synchronises,
+ * returns the summed milliseconds and launch counts per stage since the previous call, and resets. */
+int bp_set_stage_timing(bp_handle* h, int enable);
+int bp_get_stage_times(bp_handle* h, double* ms /*[BP_NSTAGE]*/, long long* launches /*[BP_NSTAGE]*/);
 
 /* Host -> HBM: replaces the pandas frames of get_market_data() (data_handling.py:270-291).  Also
  * computes both log-return matrices on the device (:37, :314). */

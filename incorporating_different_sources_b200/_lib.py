@@ -21,8 +21,10 @@ EXPORTED = [
     "bp_last_error", "bp_version", "bp_init", "bp_destroy", "bp_set_stream", "bp_synchronize",
     "bp_set_workspace_limit", "bp_device_info", "bp_launch_count", "bp_upload_market",
     "bp_prepare_market", "bp_stats_batched", "bp_hf_cov_batched", "bp_conjugate_batched",
-    "bp_jeffreys_batched",
+    "bp_jeffreys_batched", "bp_set_stage_timing", "bp_get_stage_times",
 ]
+BP_NSTAGE = 8
+STAGES = ("logret", "prep", "gram", "solve")
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -83,6 +85,8 @@ def load():
     lib.bp_hf_cov_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.c_void_p, C.c_void_p]
     lib.bp_conjugate_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.POINTER(Outputs)]
     lib.bp_jeffreys_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.POINTER(Outputs)]
+    lib.bp_set_stage_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.bp_get_stage_times.argtypes = [C.c_void_p, c_double_p, C.POINTER(C.c_longlong)]
     for name in EXPORTED:
         getattr(lib, name)          # every declared entry point must be exported
     _lib = lib

@@ -75,7 +75,37 @@ struct bp_handle {
     size_t stage_bytes = 0;
     bool need_sync = false;
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    // optional per-stage CUDA-event timing (bench.py's roofline numbers)
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<Span> spans;
 };
+
+namespace {
+struct StageTimer {
+    bp_handle* h;
+    int stage;
+    cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(bp_handle* h_, int stage_) : h(h_), stage(stage_) {
+        if (!h->timing) return;
+        while (h->ev_pool.size() < h->ev_used + 2) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            h->ev_pool.push_back(e);
+        }
+        a = h->ev_pool[h->ev_used++];
+        b = h->ev_pool[h->ev_used++];
+        cudaEventRecord(a, h->stream);
+    }
+    ~StageTimer() {
+        if (!a) return;
+        cudaEventRecord(b, h->stream);
+        h->spans.push_back({stage, a, b});
+    }
+};
+}  // namespace
 
 namespace {
 
@@ -337,6 +367,7 @@ GramParams gram_params(const bp_handle* h, const Batch& B, const Layout& L, cons
 }
 
 int run_gram(bp_handle* h, const GramParams& g) {
+    StageTimer tm(h, BP_STAGE_GRAM);
     CU_TRY(launch_gram(g, h->map_hf, h->map_d, h->sm_count, h->stream));
     h->launches++;
     return BP_OK;
@@ -369,7 +400,10 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
         const int wc = std::min(Wc, B.W - w0);
         const size_t ov = (size_t)w0 * N, om = (size_t)w0 * N * N;
         PrepParams pp = prep_params(h, b, B, L, c, w0, mode);
-        CU_TRY(launch_window_prep(pp, wc, h->stream));
+        {
+            StageTimer tm(h, BP_STAGE_PREP);
+            CU_TRY(launch_window_prep(pp, wc, h->stream));
+        }
         h->launches++;
         if (out->T) {
             rc = run_gram(h, gram_params(h, B, L, c, w0, wc, GRAM_T));
@@ -405,7 +439,10 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
             sp.nu = c.nu;
             sp.weights = c.weights;
             sp.status = c.status;
-            CU_TRY(launch_chol_solve(sp, h->sm_count, h->stream));
+            {
+                StageTimer tm(h, BP_STAGE_SOLVE);
+                CU_TRY(launch_chol_solve(sp, h->sm_count, h->stream));
+            }
             h->launches++;
             if ((rc = emit_vec(h, c.weights, L, wc, out->weights ? out->weights + ov : nullptr))) return rc;
             if ((rc = emit_vec(h, c.nu, L, wc, out->nu ? out->nu + ov : nullptr))) return rc;
@@ -472,6 +509,7 @@ int bp_destroy(bp_handle* h) {
     cudaFree(h->desc);
     cudaFree(h->ws);
     cudaFree(h->stage);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
     return BP_OK;
 }
@@ -507,15 +545,42 @@ int bp_device_info(bp_handle* h, int* sm_count, size_t* free_bytes, size_t* tota
 
 long long bp_launch_count(bp_handle* h) { return h ? h->launches : 0; }
 
+int bp_set_stage_timing(bp_handle* h, int enable) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    h->timing = enable != 0;
+    return BP_OK;
+}
+
+int bp_get_stage_times(bp_handle* h, double* ms, long long* launches) {
+    if (!h || !ms || !launches) return fail(BP_ERR_INVALID, "null argument");
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < BP_NSTAGE; ++i) {
+        ms[i] = 0.0;
+        launches[i] = 0;
+    }
+    for (const auto& sp : h->spans) {
+        float t = 0.f;
+        CU_TRY(cudaEventElapsedTime(&t, sp.a, sp.b));
+        ms[sp.stage] += (double)t;
+        launches[sp.stage] += 1;
+    }
+    h->spans.clear();
+    h->ev_used = 0;
+    return BP_OK;
+}
+
 int bp_prepare_market(bp_handle* h) {
     if (!h) return fail(BP_ERR_INVALID, "null handle");
     if (!h->has_market) return fail(BP_ERR_STATE, "no market uploaded");
     CU_TRY(cudaSetDevice(h->device));
-    launch_log_returns(h->prices, h->lr_d, h->D, h->N, h->ld, h->sm_count, h->stream);
-    h->launches++;
-    if (h->R > 0) {
-        launch_log_returns(h->hf_prices, h->lr_hf, h->R, h->N, h->ld, h->sm_count, h->stream);
+    {
+        StageTimer tm(h, BP_STAGE_LOGRET);
+        launch_log_returns(h->prices, h->lr_d, h->D, h->N, h->ld, h->sm_count, h->stream);
         h->launches++;
+        if (h->R > 0) {
+            launch_log_returns(h->hf_prices, h->lr_hf, h->R, h->N, h->ld, h->sm_count, h->stream);
+            h->launches++;
+        }
     }
     CU_TRY(cudaGetLastError());
     return BP_OK;

@@ -102,6 +102,20 @@ class BayesEngine:
             _raise(rc)
         return {"sm_count": sm.value, "free_bytes": fr.value, "total_bytes": tot.value}
 
+    def set_stage_timing(self, enable: bool):
+        rc = self._lib.bp_set_stage_timing(self._h, int(bool(enable)))
+        if rc:
+            _raise(rc)
+
+    def stage_times(self) -> Dict[str, Dict[str, float]]:
+        """Summed CUDA-event milliseconds and launch counts per stage since the last call."""
+        ms = (C.c_double * _lib.BP_NSTAGE)()
+        cnt = (C.c_longlong * _lib.BP_NSTAGE)()
+        rc = self._lib.bp_get_stage_times(self._h, ms, cnt)
+        if rc:
+            _raise(rc)
+        return {name: {"ms": ms[i], "launches": int(cnt[i])} for i, name in enumerate(_lib.STAGES)}
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.bp_launch_count(self._h))

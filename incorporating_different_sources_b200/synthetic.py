@@ -122,7 +122,10 @@ def generate_market(
     N, D, B = n_assets, n_days, bars_per_day
     dates = business_days(start, D)
 
-    # factor loadings / idiosyncratic vols / drifts (per day)
+    # Only exactly-rounded elementwise arithmetic and sequential cumulative products are used below
+    # (no BLAS matmul, no exp/sin/log ufuncs): the same seed must give bit-identical arrays on the
+    # build container and on the GPU box, whose CPUs / BLAS thread counts differ.  The golden
+    # fixtures store SHA-256 prefixes of these arrays and the tests refuse to run on a mismatch.
     beta = rng.normal(0.0, 1.0, size=(n_factors, N))
     beta[0] = np.abs(beta[0]) * 0.5 + 0.6          # market factor: all positive
     fvol = np.concatenate([[0.010], np.full(n_factors - 1, 0.004)])
@@ -130,16 +133,17 @@ def generate_market(
     drift = rng.uniform(1e-4, 7e-4, size=N)
 
     rows = D * B
-    sb = 1.0 / np.sqrt(B)
-    # intraday log returns: idiosyncratic + factor part
+    sb = 1.0 / float(np.sqrt(float(B)))
+    # intraday simple returns: idiosyncratic + factor part (+ drift); price = cumulative product
     r = rng.standard_normal(size=(rows, N))
     r *= ivol * sb
-    f = rng.standard_normal(size=(rows, n_factors)) * (fvol * sb)
-    r += f @ beta
+    f = rng.standard_normal(size=(rows, n_factors))
+    for k in range(n_factors):
+        r += (f[:, k:k + 1] * (fvol[k] * sb)) * beta[k]
     r += drift / B
-    np.cumsum(r, axis=0, out=r)
+    r += 1.0
+    np.cumprod(r, axis=0, out=r)
     p0 = rng.uniform(20.0, 400.0, size=N)
-    np.exp(r, out=r)
     r *= p0
     hf_prices = r
     prices = np.ascontiguousarray(hf_prices[B - 1 :: B])      # close = last bar of the day
@@ -153,20 +157,24 @@ def generate_market(
     bar_off = (_FIRST_BAR_MIN + 5 * np.arange(B)) * _NS_PER_MIN
     hf_ts = (day_ns[:, None] + bar_off[None, :]).reshape(-1).astype("datetime64[ns]")
 
-    tt = np.arange(D)
+    tt = np.arange(D, dtype=np.float64)
+
+    def tri(x):                                    # triangle wave in [-1, 1], arithmetic only
+        fr = x - np.floor(x)
+        return 2.0 * np.abs(2.0 * fr - 1.0) - 1.0
+
     if mcm_mode == "constant":
         vix = np.full(D, 20.0)
         epu = np.full(D, 100.0)
     else:
-        vix = 20.0 * np.exp(0.35 * np.sin(2 * np.pi * tt / 517.0) + 0.08 * rng.standard_normal(D))
-        epu = 100.0 * np.exp(0.45 * np.sin(2 * np.pi * tt / 731.0 + 1.0) + 0.15 * rng.standard_normal(D))
+        vix = 20.0 * (1.0 + 0.35 * tri(tt / 517.0)) * (1.0 + 0.08 * np.clip(rng.standard_normal(D), -3, 3))
+        epu = 100.0 * (1.0 + 0.45 * tri(tt / 731.0 + 0.3)) * (1.0 + 0.12 * np.clip(rng.standard_normal(D), -3, 3))
     if rf_mode == "constant":
         rf = np.full(D, 0.02)
     else:
-        rf = 0.025 + 0.024 * np.sin(2 * np.pi * tt / 1900.0) + 0.0005 * rng.standard_normal(D)
+        rf = 0.025 + 0.024 * tri(tt / 1900.0) + 0.0005 * rng.standard_normal(D)
         rf = np.clip(rf, 0.0, 0.05)
-    mkt = np.exp(np.cumsum(rng.normal(3e-4, 0.011, size=D)))
-    sp500 = 1200.0 * mkt
+    sp500 = 1200.0 * np.cumprod(1.0 + rng.normal(3e-4, 0.011, size=D))
 
     return SyntheticMarket(
         tickers=make_tickers(N),
