@@ -1,0 +1,456 @@
+#!/usr/bin/env python
+"""Benchmark of the rolling-window Bayesian tangency-weight hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], "C2"): one full daily-rebalance backtest, 4,150 rebalance dates,
+N = 500 synthetic assets, conjugate (VIX-scaled HF prior) + Jeffreys priors = 8,300 windows per step:
+  * conjugate: 252-day daily window + 5-minute intraday prior over the reference's 7-calendar-day
+    look-back (389 HF returns).  The reference's own 1-day look-back is rank deficient at N = 500
+    (rank <= 76 + 251 < 500), so the well-posed look-back from its table (:299-304) is used,
+    which the reference itself reaches through ``conjugate_prior_S_df=``;
+  * Jeffreys: rolling_window = 1008 (n-1 >= N is required for T - tt'/n to be non-singular).
+A "step" is one pass of the whole path over that backtest: log returns, per-window reductions and
+prior scalars, batched Gram (DMMA), batched Cholesky solve, weights.  ``value`` times it with the
+prices already resident in HBM; ``e2e`` times the public host-buffer API including the host->device
+copy of the market and the device->host read of the weights.  N > 1 GPUs: weak scaling, one
+independent synthetic path per rank (BASELINE configs[4]), weights all-gathered with NCCL.
+
+``--impl reference`` times the CPU oracle port (oracle/bayes_oracle.py, the NumPy restatement of the
+reference's algorithm; the reference itself is pandas code that cannot travel to the GPU box) on a
+bounded sample of the same windows with every host core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "posterior tangency-weight windows/sec at N=500"
+UNIT = "windows/s"
+
+
+# ----------------------------------------------------------------------------- workload
+def make_specs(n_assets):
+    conj = dict(weighting_strategy="conjugate_hf_vix_vw", size=n_assets, risk_aversion=5, turnover_cost=15,
+                rebalancing_frequency="daily", rolling_window=252, rolling_window_frequency="daily",
+                mcm_scaling=1, display_name="Conjugate HF-VIX VW")
+    jeff = dict(conj, weighting_strategy="jeffreys", mcm_scaling=None, rolling_window=max(1008, 2 * n_assets + 8),
+                display_name="Jeffreys")
+    return conj, jeff
+
+
+def make_workload(args, path):
+    from incorporating_different_sources_b200.synthetic import generate_market
+    conj, jeff = make_specs(args.n_assets)
+    n_long = jeff["rolling_window"]
+    n_days = n_long + args.windows - 1
+    start = str(np.busday_offset(np.datetime64("2007-01-01"), -(n_long - 1), roll="forward"))
+    mkt = generate_market(args.n_assets, n_days, seed=1000 * path + 2, start=start)
+    d_idx = np.arange(n_long - 1, n_days)
+    return mkt, conj, jeff, d_idx
+
+
+def config_dict(args, n_gpus, conj, jeff, hf_days):
+    return {
+        "workload": "C2: full daily-rebalance backtest, conjugate(VIX)+Jeffreys, synthetic S&P-500-sized universe",
+        "n_assets": args.n_assets, "rebalance_dates": args.windows, "windows_per_step_per_gpu": 2 * args.windows,
+        "conjugate": {"rolling_window": conj["rolling_window"], "hf_lookback_calendar_days": hf_days,
+                      "hf_bar_minutes": 5, "prior": "vw", "mcm": "VIX"},
+        "jeffreys": {"rolling_window": jeff["rolling_window"]},
+        "sharding": f"{n_gpus} independent synthetic path(s), one per GPU; weights all-gathered (NCCL)" if n_gpus > 1
+        else "single GPU, one path",
+        "cache": "inputs larger than L2 (1.6 GB intraday prices, 8.8 GB workspace); no flush needed",
+    }
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- flops / bytes
+def algorithmic_work(N, W, n_c, m_hf, n_j):
+    """SURVEY §8(d) conventions: full-matrix DGEMM flops; compulsory bytes."""
+    gram_conj = 2.0 * N * N * ((n_c - 1) + m_hf)
+    gram_jeff = 2.0 * N * N * (n_j - 1)
+    chol = N ** 3 / 3.0 + 4.0 * N * N
+    return {
+        "gram_flops": W * (gram_conj + gram_jeff),
+        "solve_flops": 2 * W * chol,
+        "solve_bytes": 2 * W * (8.0 * N * N + 16.0 * N),
+        "prep_bytes": W * 8.0 * N * ((n_c - 1) + 2 * m_hf + (n_j - 1)),
+    }
+
+
+# ----------------------------------------------------------------------------- reference arm
+_G = {}
+
+
+def _ref_window(job):
+    from oracle import bayes_oracle as bo
+    kind, d = job
+    mkt, conj, jeff, cols, hf_days = _G["mkt"], _G["conj"], _G["jeff"], _G["cols"], _G["hf_days"]
+    if kind == 0:
+        return bo.conjugate_window(conj, mkt, d, cols, hf_lookback_days=hf_days)["weights"][:4]
+    return bo.jeffreys_window(jeff, mkt, d, cols)["weights"][:4]
+
+
+def run_reference(args):
+    """CPU arm: the oracle port on every host core, bounded sample of the same windows per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        threadpool_limits = None
+    mkt, conj, jeff, d_idx = make_workload(args, 0)
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    per_step = max(2 * procs, args.ref_sample)
+    per_step -= per_step % 2
+    sel = np.linspace(0, len(d_idx) - 1, per_step // 2).round().astype(int)
+    jobs = [(0, int(d_idx[i])) for i in sel] + [(1, int(d_idx[i])) for i in sel]
+    _G.update(mkt=mkt, conj=conj, jeff=jeff, cols=np.arange(args.n_assets), hf_days=args.hf_days)
+    ctx = mp.get_context("fork")
+    if threadpool_limits:
+        threadpool_limits(1)          # one BLAS thread per worker process: windows are independent
+    with ctx.Pool(procs) as pool:
+        for _ in range(args.warmup):
+            pool.map(_ref_window, jobs, chunksize=1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_ref_window, jobs, chunksize=1)
+        dt = (time.perf_counter() - t0) / args.steps
+    value = len(jobs) / dt
+    sample = (f"{len(jobs)} windows per step ({len(jobs)//2} conjugate + {len(jobs)//2} Jeffreys, stratified over the "
+              f"{args.windows} rebalance dates), {procs} worker processes x 1 BLAS thread")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, 1, conj, jeff, args.hf_days),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "oracle/bayes_oracle.py (NumPy restatement of the reference's algorithm, pinned to the reference's "
+                "outputs by tests/golden); the pandas reference itself cannot travel to the GPU box",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def measure_dgemm_peak(torch, dev):
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    best = 1e30
+    for i in range(6):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        c = a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        if i:
+            best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from incorporating_different_sources_b200.engine import BayesEngine, upload_synthetic
+    from incorporating_different_sources_b200.windows import ffill_rows, plan_daily_windows
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dgemm_tf = measure_dgemm_peak(torch, dev)
+
+    mkt, conj, jeff, d_idx = make_workload(args, rank)
+    N, W = args.n_assets, len(d_idx)
+    eng = BayesEngine(local)
+    # pinned host copies of the inputs (the e2e leg copies them every step)
+    def pin(a):
+        t = torch.empty(a.shape, dtype=torch.float64).pin_memory()
+        v = t.numpy()
+        v[...] = a
+        return t, v
+    keep = []
+    host = {}
+    for name, arr in (("prices", mkt.prices), ("caps", mkt.caps), ("hf_prices", mkt.hf_prices),
+                      ("mcm", np.stack([mkt.vix, mkt.epu])), ("rf_row", ffill_rows(mkt.dates, mkt.dates, mkt.rf))):
+        t, v = pin(arr)
+        keep.append(t)
+        host[name] = v
+    h2d_bytes = int(sum(v.nbytes for v in host.values()))
+    cb = plan_daily_windows(conj, mkt.dates, d_idx, mkt.hf_ts, hf_lookback_days=args.hf_days)
+    jb = plan_daily_windows(jeff, mkt.dates, d_idx, need_hf=False)
+    m_hf = int((cb.hf_hi - cb.hf_lo - 1).max())
+
+    eng.upload_market(**host)
+    out_c = {"weights": torch.empty((W, N), dtype=torch.float64, device=dev),
+             "status": torch.empty((W,), dtype=torch.int32, device=dev)}
+    out_j = {"weights": torch.empty((W, N), dtype=torch.float64, device=dev),
+             "status": torch.empty((W,), dtype=torch.int32, device=dev)}
+    gathered = None
+    if world > 1:
+        gathered = torch.empty((world, 2, W, N), dtype=torch.float64, device=dev)
+        mine = torch.empty((2, W, N), dtype=torch.float64, device=dev)
+
+    def step_device():
+        eng.prepare_market()
+        eng.conjugate(cb, outputs=("weights", "status"), into=out_c)
+        eng.jeffreys(jb, outputs=("weights", "status"), into=out_j)
+        if world > 1:
+            mine[0].copy_(out_c["weights"])
+            mine[1].copy_(out_j["weights"])
+            dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))
+
+    hw_c, hw_cv = pin(np.zeros((W, N)))
+    hw_j, hw_jv = pin(np.zeros((W, N)))
+    hs_c = np.zeros(W, dtype=np.int32)
+    hs_j = np.zeros(W, dtype=np.int32)
+    d2h_bytes = int(hw_cv.nbytes + hw_jv.nbytes + hs_c.nbytes + hs_j.nbytes)
+
+    def step_e2e():
+        eng.upload_market(**host)
+        eng.conjugate(cb, outputs=("weights", "status"), into={"weights": hw_cv, "status": hs_c})
+        eng.jeffreys(jb, outputs=("weights", "status"), into={"weights": hw_jv, "status": hs_j})
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    eng.set_stage_timing(True)
+    eng.stage_times()
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    stages = eng.stage_times()
+    eng.set_stage_timing(False)
+    launches = (eng.launch_count - launches0) // args.steps + (3 if world > 1 else 0)
+    status_bad = int((out_c["status"] != 0).sum().item() + (out_j["status"] != 0).sum().item())
+    value = n_gpus * 2 * W / (ms * 1e-3)
+
+    # ---- end-to-end timing through the host-buffer API
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e_value = n_gpus * 2 * W / e2e_s
+    e2e_match = bool(np.array_equal(hw_cv, out_c["weights"].cpu().numpy()))
+
+    if rank == 0:
+        work = algorithmic_work(N, W, conj["rolling_window"], m_hf, jeff["rolling_window"])
+        k = args.steps
+        g_ms = stages["gram"]["ms"] / k
+        s_ms = stages["solve"]["ms"] / k
+        p_ms = stages["prep"]["ms"] / k
+        l_ms = stages["logret"]["ms"] / k
+        gram_tf = work["gram_flops"] / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "gram_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        logret_bytes = 2 * 8.0 * (mkt.prices.shape[0] + mkt.hf_prices.shape[0]) * eng_ld(N)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, n_gpus, conj, jeff, args.hf_days),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_s * 1e3, "matches_device_path": e2e_match},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "kernel": "gram_dmma_kernel (2 launches per step: conjugate S1, Jeffreys J)",
+                "bound": "tensor", "achieved": gram_tf, "peak": dgemm_tf, "unit": "TFLOP/s",
+                "frac": gram_tf / dgemm_tf if dgemm_tf > 0 else None, "traffic": traffic,
+                "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul f64) measured live in this run; "
+                               "MEASURED_PEAKS.json has no FP64 figure",
+                "flops_convention": "full-matrix 2*N^2*K per window (SURVEY 8(d)); the kernel computes lower-triangular "
+                                    "128x128 tiles only (10 of 16 at N=500)",
+                "ms_per_step": g_ms, "share_of_step": g_ms / ms if ms > 0 else None,
+            },
+            "stages": {
+                "logret": {"ms": l_ms, "bound": "hbm", "achieved_gbs": logret_bytes / (l_ms * 1e-3) / 1e9 if l_ms > 0 else None,
+                           "peak_gbs": hbm_peak, "peak_source": hbm_src},
+                "prep": {"ms": p_ms, "bound": "hbm", "achieved_gbs": work["prep_bytes"] / (p_ms * 1e-3) / 1e9 if p_ms > 0 else None,
+                         "peak_gbs": hbm_peak, "note": "algorithmic bytes: each window charged its own rows; served mostly from L2"},
+                "solve": {"ms": s_ms, "bound": "tensor+hbm",
+                          "achieved_tflops": work["solve_flops"] / (s_ms * 1e-3) / 1e12 if s_ms > 0 else None,
+                          "achieved_gbs": work["solve_bytes"] / (s_ms * 1e-3) / 1e9 if s_ms > 0 else None,
+                          "peak_tflops": dgemm_tf, "peak_gbs": hbm_peak},
+            },
+            "windows_flagged_singular": status_bad,
+        }
+        if n_gpus == 1 and not args.no_cpu:
+            line["cpu_baseline"], line["parity_max_rel_err"] = cpu_baseline(args, mkt, conj, jeff, d_idx, out_c, out_j)
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def eng_ld(N):
+    return (N + 15) // 16 * 16
+
+
+def cpu_baseline(args, mkt, conj, jeff, d_idx, out_c, out_j):
+    """Oracle port on the box's host cores over a bounded, stratified sample; doubles as a parity check."""
+    from oracle import bayes_oracle as bo
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = 1
+    n = max(2, args.cpu_sample // 2)
+    sel = np.linspace(0, len(d_idx) - 1, n).round().astype(int)
+    cols = np.arange(args.n_assets)
+    wc = out_c["weights"].cpu().numpy()
+    wj = out_j["weights"].cpu().numpy()
+    worst = 0.0
+    t0 = time.perf_counter()
+    for i in sel:
+        r = bo.conjugate_window(conj, mkt, int(d_idx[i]), cols, hf_lookback_days=args.hf_days)["weights"]
+        worst = max(worst, float(np.max(np.abs(wc[i] - r)) / np.max(np.abs(r))))
+        r = bo.jeffreys_window(jeff, mkt, int(d_idx[i]), cols)["weights"]
+        worst = max(worst, float(np.max(np.abs(wj[i] - r)) / np.max(np.abs(r))))
+    dt = time.perf_counter() - t0
+    return ({"value": 2 * n / dt, "unit": UNIT, "cores": int(threads), "kind": "port",
+             "sample": f"{2 * n} windows ({n} conjugate + {n} Jeffreys, stratified over the {len(d_idx)} rebalance dates), "
+                       f"oracle/bayes_oracle.py with NumPy's default BLAS threads ({threads})"}, worst)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-assets", type=int, default=500)
+    ap.add_argument("--windows", type=int, default=4150)
+    ap.add_argument("--hf-days", type=int, default=7)
+    ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--ref-sample", type=int, default=128)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
