@@ -43,6 +43,7 @@ extern "C" {
 #define BP_SCAL_M 6           /* number of HF returns m        :314                                  */
 #define BP_SCAL_SUMA 7        /* sum of risk-free adjustments  :48                                   */
 #define BP_SCAL_V1 8          /* w1' S1 w1                     :574                                  */
+#define BP_SCAL_MCM_AVG 9     /* average MCM over the window   :112                                  */
 
 /* stages reported by bp_get_stage_times */
 #define BP_NSTAGE 8
@@ -80,6 +81,9 @@ typedef struct {
     double mcm_scaling;         /* spec["mcm_scaling"] (:265)                                        */
     double risk_aversion;       /* spec["risk_aversion"] (:836,:849)                                 */
     int prior_weights;          /* 0: value weighted ("vw" in strategy, :369) 1: equally weighted    */
+    int mcm_rows;               /* MCM observations averaged; 0 = rolling_window (iloc[-n:], :112)   */
+    const double* prior_n;      /* [W] injected conjugate_prior_n (the reference's conjugate_prior_n=
+                                   argument, :289,:388,:507) or NULL: derive n0 from the MCM series  */
 } bp_window_batch;
 
 /* Optional outputs (NULL = not wanted).  Vectors are [W][N], matrices [W][N][N] dense symmetric. */
@@ -132,6 +136,50 @@ int bp_hf_cov_batched(bp_handle* h, const bp_window_batch* b, double* n0, double
 int bp_conjugate_batched(bp_handle* h, const bp_window_batch* b, const bp_outputs* out);
 /* calculate_jeffreys_portfolio (:838-849) for W windows. */
 int bp_jeffreys_batched(bp_handle* h, const bp_window_batch* b, const bp_outputs* out);
+
+/* The posterior MOMENTS of W windows without the solve: any of t, w0, rhs, scalars (n0, n1, c, v0, MCM
+ * average), T, S0, S1 (mode 0: conjugate S1 = S0 + T, :335-358; mode 1: Jeffreys T - tt'/n, :600-601).
+ * Backs calculate_average_mcm_window / calculate_conjugate_prior_n / _posterior_n / _prior_w /
+ * _posterior_S / calculate_conjugate_c when nothing is injected (:90-114, :247-430). */
+int bp_moments_batched(bp_handle* h, const bp_window_batch* b, int mode, const bp_outputs* out);
+
+/* calculate_excess_log_returns_from_prices (:31-62) of ONE window (b->n_windows == 1):
+ * X is [(rolling_window-1)][N]. */
+int bp_excess_returns(bp_handle* h, const bp_window_batch* b, double* X);
+
+/* calculate_portfolio_variance (:64-88): *out = w' S w for dense S [n][n] (host pointers). */
+int bp_quadratic_form(bp_handle* h, int n, const double* w, const double* S, double* out);
+
+/* Single-window posterior from DENSE, possibly caller-injected moments: the optional-argument forms of
+ * calculate_conjugate_c / _posterior_S / _posterior_w / calculate_mean_conjugate_posterior_nu (:382-577)
+ * and calculate_mean_jeffreys_posterior_nu (:580-608).  All pointers are host pointers. */
+typedef struct {
+    int n_assets;
+    int jeffreys;               /* 0 conjugate, 1 Jeffreys                                           */
+    int rolling_window;         /* n                                                                 */
+    double risk_aversion;
+    const double* T;            /* [N][N] canonical statistic T; NULL (with t NULL): only v0 and c
+                                   are computed (calculate_conjugate_c with injected moments)        */
+    const double* t;            /* [N]                                                               */
+    const double* S0;           /* [N][N] conjugate prior S        (conjugate only)                  */
+    const double* w0;           /* [N]    prior weights            (conjugate only)                  */
+    double n0;                  /* conjugate prior n                                                 */
+    const double* n1;           /* optional injected posterior n   (NULL: n0 + n)                    */
+    const double* c;            /* optional injected conjugate_c                                     */
+    const double* S1;           /* optional injected posterior S [N][N]                              */
+    const double* w1;           /* optional injected posterior w [N]                                 */
+} bp_dense_problem;
+
+typedef struct {
+    double* scalars;            /* [BP_NSCAL] n0, n1, c, v0, v1                                       */
+    double* S1;                 /* [N][N]                                                            */
+    double* w1;                 /* [N]                                                               */
+    double* nu;                 /* [N]                                                               */
+    double* weights;            /* [N]                                                               */
+    int* status;                /* [1]                                                               */
+} bp_dense_result;
+
+int bp_dense_posterior(bp_handle* h, const bp_dense_problem* in, const bp_dense_result* out);
 
 #ifdef __cplusplus
 }

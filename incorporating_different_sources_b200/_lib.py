@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbayes_portfolio.so")
 
 BP_NSCAL = 12
-SCAL = dict(n0=0, n1=1, alpha=2, beta=3, c=4, v0=5, m=6, sum_a=7, v1=8)
+SCAL = dict(n0=0, n1=1, alpha=2, beta=3, c=4, v0=5, m=6, sum_a=7, v1=8, mcm_avg=9)
 
 BP_OK, BP_ERR_INVALID, BP_ERR_CUDA, BP_ERR_NO_DEVICE, BP_ERR_STATE = 0, 1, 2, 3, 4
 
@@ -22,6 +22,7 @@ EXPORTED = [
     "bp_set_workspace_limit", "bp_device_info", "bp_launch_count", "bp_upload_market",
     "bp_prepare_market", "bp_stats_batched", "bp_hf_cov_batched", "bp_conjugate_batched",
     "bp_jeffreys_batched", "bp_set_stage_timing", "bp_get_stage_times",
+    "bp_excess_returns", "bp_quadratic_form", "bp_dense_posterior", "bp_moments_batched",
 ]
 BP_NSTAGE = 8
 STAGES = ("logret", "prep", "gram", "solve")
@@ -43,13 +44,25 @@ class WindowBatchDesc(C.Structure):
         ("n_windows", C.c_int), ("rolling_window", C.c_int),
         ("day_row", C.c_void_p), ("span_days", C.c_void_p), ("hf_lo", C.c_void_p), ("hf_hi", C.c_void_p),
         ("mcm_index", C.c_int), ("mcm_scaling", C.c_double), ("risk_aversion", C.c_double),
-        ("prior_weights", C.c_int),
+        ("prior_weights", C.c_int), ("mcm_rows", C.c_int), ("prior_n", C.c_void_p),
     ]
 
 
 class Outputs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in
                 ("weights", "nu", "w1", "t", "w0", "rhs", "scalars", "status", "T", "S0", "S1")]
+
+
+class DenseProblem(C.Structure):
+    _fields_ = [
+        ("n_assets", C.c_int), ("jeffreys", C.c_int), ("rolling_window", C.c_int), ("risk_aversion", C.c_double),
+        ("T", C.c_void_p), ("t", C.c_void_p), ("S0", C.c_void_p), ("w0", C.c_void_p), ("n0", C.c_double),
+        ("n1", C.c_void_p), ("c", C.c_void_p), ("S1", C.c_void_p), ("w1", C.c_void_p),
+    ]
+
+
+class DenseResult(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("scalars", "S1", "w1", "nu", "weights", "status")]
 
 
 class LibraryMissing(RuntimeError):
@@ -87,6 +100,10 @@ def load():
     lib.bp_jeffreys_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.POINTER(Outputs)]
     lib.bp_set_stage_timing.argtypes = [C.c_void_p, C.c_int]
     lib.bp_get_stage_times.argtypes = [C.c_void_p, c_double_p, C.POINTER(C.c_longlong)]
+    lib.bp_moments_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.c_int, C.POINTER(Outputs)]
+    lib.bp_excess_returns.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.c_void_p]
+    lib.bp_quadratic_form.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bp_dense_posterior.argtypes = [C.c_void_p, C.POINTER(DenseProblem), C.POINTER(DenseResult)]
     for name in EXPORTED:
         getattr(lib, name)          # every declared entry point must be exported
     _lib = lib

@@ -68,6 +68,8 @@ struct bp_handle {
     // window descriptors on the device: day_row, span, row0, hf_row0, hf_m
     int* desc = nullptr;
     int desc_cap = 0;
+    double* prior_n = nullptr;
+    int prior_n_cap = 0;
     // workspace
     unsigned char* ws = nullptr;
     size_t ws_bytes = 0;
@@ -200,6 +202,8 @@ struct Batch {
     int W = 0, n = 0, max_m = 0;
     bool has_hf = false;
     const int *day_row = nullptr, *span = nullptr, *row0 = nullptr, *hf_row0 = nullptr, *hf_m = nullptr;
+    const double* prior_n = nullptr;
+    int mcm_rows = 0;
 };
 
 int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* out) {
@@ -212,7 +216,9 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
     if (need_hf) {
         if (!b->hf_lo || !b->hf_hi) return fail(BP_ERR_INVALID, "hf_lo / hf_hi missing");
         if (h->R <= 0) return fail(BP_ERR_STATE, "the uploaded market has no intraday prices");
-        if (b->mcm_index < 0 || b->mcm_index >= h->n_mcm) return fail(BP_ERR_INVALID, "mcm_index %d out of range", b->mcm_index);
+        if (!b->prior_n && (b->mcm_index < 0 || b->mcm_index >= h->n_mcm))
+            return fail(BP_ERR_INVALID, "mcm_index %d out of range", b->mcm_index);
+        if (b->mcm_rows < 0 || b->mcm_rows > n) return fail(BP_ERR_INVALID, "mcm_rows must be in [0, rolling_window]");
         if (b->prior_weights == 0 && !h->caps) return fail(BP_ERR_STATE, "value-weighted prior needs market caps");
     }
     std::vector<int> host((size_t)5 * W, 0);
@@ -221,6 +227,8 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         const int dr = b->day_row[w];
         if (dr < n - 1 || dr >= h->D)
             return fail(BP_ERR_INVALID, "window %d: day_row %d needs %d prior price rows inside [0,%d)", w, dr, n - 1, h->D);
+        if (need_hf && !b->prior_n && dr < (b->mcm_rows ? b->mcm_rows : n) - 1)
+            return fail(BP_ERR_INVALID, "window %d: not enough MCM observations before day_row %d", w, dr);
         if (b->span_days[w] <= 0) return fail(BP_ERR_INVALID, "window %d: span_days must be positive", w);
         host[w] = dr;
         host[(size_t)W + w] = b->span_days[w];
@@ -248,6 +256,19 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
     // the staging vector dies at return: make the copy complete before that
     CU_TRY(cudaMemcpyAsync(h->desc, host.data(), sizeof(int) * 5 * (size_t)W, cudaMemcpyHostToDevice, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
+    if (need_hf && b->prior_n) {
+        if (W > h->prior_n_cap) {
+            cudaFree(h->prior_n);
+            h->prior_n = nullptr;
+            h->prior_n_cap = 0;
+            CU_TRY(cudaMalloc(&h->prior_n, sizeof(double) * (size_t)W));
+            h->prior_n_cap = W;
+        }
+        CU_TRY(cudaMemcpyAsync(h->prior_n, b->prior_n, sizeof(double) * (size_t)W, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        out->prior_n = h->prior_n;
+    }
+    out->mcm_rows = b->mcm_rows ? b->mcm_rows : n;
     out->W = W;
     out->n = n;
     out->max_m = max_m;
@@ -319,7 +340,9 @@ PrepParams prep_params(const bp_handle* h, const bp_window_batch* b, const Batch
     p.lr_daily = h->lr_d;
     p.lr_hf = h->lr_hf;
     p.caps = h->caps;
-    p.mcm = (mode == BP_MODE_CONJUGATE) ? h->mcm + (size_t)b->mcm_index * h->D : nullptr;
+    p.mcm = (mode == BP_MODE_CONJUGATE && h->mcm) ? h->mcm + (size_t)b->mcm_index * h->D : nullptr;
+    p.mcm_rows = B.mcm_rows;
+    p.prior_n = B.prior_n ? B.prior_n + w0 : nullptr;
     p.rf_row = h->rf_row;
     p.day_row = B.day_row + w0;
     p.span_days = B.span + w0;
@@ -507,6 +530,7 @@ int bp_destroy(bp_handle* h) {
     cudaStreamSynchronize(h->stream);
     free_market(h);
     cudaFree(h->desc);
+    cudaFree(h->prior_n);
     cudaFree(h->ws);
     cudaFree(h->stage);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -669,6 +693,144 @@ int bp_hf_cov_batched(bp_handle* h, const bp_window_batch* b, double* n0, double
         if (is_device_ptr(n0)) return fail(BP_ERR_INVALID, "bp_hf_cov_batched: n0 must be a host pointer");
         for (int w = 0; w < b->n_windows; ++w) n0[w] = scal[(size_t)w * BP_NSCAL + BP_SCAL_N0];
     }
+    return BP_OK;
+}
+
+int bp_moments_batched(bp_handle* h, const bp_window_batch* b, int mode, const bp_outputs* out) {
+    if (!out) return fail(BP_ERR_INVALID, "outputs missing");
+    if (mode != BP_MODE_CONJUGATE && mode != BP_MODE_JEFFREYS) return fail(BP_ERR_INVALID, "mode must be 0 or 1");
+    if (out->weights || out->nu || out->w1 || out->status)
+        return fail(BP_ERR_INVALID, "bp_moments_batched does not solve: use bp_conjugate_batched / bp_jeffreys_batched");
+    return run_batches(h, b, out, mode, false);
+}
+
+int bp_excess_returns(bp_handle* h, const bp_window_batch* b, double* X) {
+    if (!h || !b || !X) return fail(BP_ERR_INVALID, "null argument");
+    if (b->n_windows != 1) return fail(BP_ERR_INVALID, "bp_excess_returns handles one window per call");
+    Batch B;
+    int rc = upload_batch(h, b, false, &B);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(h->device));
+    const int K = b->rolling_window - 1;
+    const size_t bytes = sizeof(double) * (size_t)K * h->N;
+    const bool dev = is_device_ptr(X);
+    double* dst = X;
+    if (!dev) {
+        if ((rc = ensure_stage(h, bytes))) return rc;
+        dst = reinterpret_cast<double*>(h->stage);
+    }
+    launch_excess_returns(h->lr_d, h->ld, h->rf_row, b->day_row[0], b->span_days[0], b->rolling_window, h->N, dst, h->stream);
+    h->launches++;
+    CU_TRY(cudaGetLastError());
+    if (!dev) {
+        CU_TRY(cudaMemcpyAsync(X, dst, bytes, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return BP_OK;
+}
+
+int bp_quadratic_form(bp_handle* h, int n, const double* w, const double* S, double* out) {
+    if (!h || !w || !S || !out || n <= 0) return fail(BP_ERR_INVALID, "bad argument");
+    CU_TRY(cudaSetDevice(h->device));
+    const size_t need = sizeof(double) * ((size_t)n * n + n + 8);
+    int rc = ensure_stage(h, need);
+    if (rc) return rc;
+    double* dS = reinterpret_cast<double*>(h->stage);
+    double* dw = dS + (size_t)n * n;
+    double* dv = dw + n;
+    CU_TRY(cudaMemcpyAsync(dS, S, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(dw, w, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    launch_quadform(dS, n, dw, n, dv, 0.0, 0.0, nullptr, nullptr, h->stream);
+    h->launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out, dv, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return BP_OK;
+}
+
+int bp_dense_posterior(bp_handle* h, const bp_dense_problem* in, const bp_dense_result* out) {
+    if (!h || !in || !out) return fail(BP_ERR_INVALID, "null argument");
+    const int N = in->n_assets;
+    const bool c_only = !in->T && !in->t && !in->jeffreys;
+    if (N <= 0 || (!c_only && (!in->T || !in->t))) return fail(BP_ERR_INVALID, "T and t are required");
+    if (!in->jeffreys && (!in->S0 || !in->w0)) return fail(BP_ERR_INVALID, "conjugate posterior needs S0 and w0");
+    if (!(in->risk_aversion != 0.0)) return fail(BP_ERR_INVALID, "risk_aversion must be non-zero");
+    CU_TRY(cudaSetDevice(h->device));
+    const int ldS = round_up(N, 32), rowsS = ldS + 8, ldv = round_up(N, 16);
+    const size_t NN = (size_t)N * N;
+    auto al = [](size_t x) { return (x + 3) & ~(size_t)3; };      // keep every carve 32-byte aligned
+    const size_t doubles = 3 * al(NN) + 4 * al(N) + 4 * al(ldv) + (size_t)rowsS * ldS + al(BP_NSCAL) + 8;
+    int rc = ensure_ws(h, sizeof(double) * doubles + 64);
+    if (rc) return rc;
+    double* p = reinterpret_cast<double*>(h->ws);
+    double* dT = p;            p += al(NN);
+    double* dS0 = p;           p += al(NN);
+    double* dS1in = p;         p += al(NN);
+    double* dt = p;            p += al(N);
+    double* dw0 = p;           p += al(N);
+    double* dw1in = p;         p += al(N);
+    double* ds0w0 = p;         p += al(N);
+    double* drhs = p;          p += al(ldv);
+    double* dw1 = p;           p += al(ldv);
+    double* dnu = p;           p += al(ldv);
+    double* dwts = p;          p += al(ldv);
+    double* dscal = p;         p += al(BP_NSCAL);
+    double* dS = p;            p += (size_t)rowsS * ldS;
+    int* dstatus = reinterpret_cast<int*>(p);
+    cudaStream_t st = h->stream;
+    CU_TRY(cudaMemsetAsync(dscal, 0, sizeof(double) * BP_NSCAL, st));
+    CU_TRY(cudaMemsetAsync(dstatus, 0, sizeof(int), st));
+    if (!c_only) {
+        CU_TRY(cudaMemcpyAsync(dT, in->T, sizeof(double) * NN, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(dt, in->t, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    }
+    if (!in->jeffreys) {
+        CU_TRY(cudaMemcpyAsync(dS0, in->S0, sizeof(double) * NN, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(dw0, in->w0, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+        if (in->S1) CU_TRY(cudaMemcpyAsync(dS1in, in->S1, sizeof(double) * NN, cudaMemcpyHostToDevice, st));
+        if (in->w1) CU_TRY(cudaMemcpyAsync(dw1in, in->w1, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    }
+    const double n1 = in->n1 ? *in->n1 : in->n0 + (double)in->rolling_window;
+    DenseParams dp{};
+    dp.n_assets = N; dp.ldS = ldS; dp.ldv = ldv; dp.n_window = in->rolling_window;
+    dp.n0 = in->n0; dp.n1 = n1; dp.has_c = in->c != nullptr; dp.c_in = in->c ? *in->c : 0.0;
+    dp.T = c_only ? nullptr : dT; dp.t = c_only ? nullptr : dt; dp.S0 = dS0; dp.w0 = dw0; dp.S1_in = (!in->jeffreys && in->S1) ? dS1in : nullptr;
+    dp.s0w0 = ds0w0; dp.rhs = drhs; dp.S_out = dS; dp.scal = dscal;
+    launch_dense_prep(dp, in->jeffreys != 0, st);
+    h->launches++;
+    CU_TRY(cudaGetLastError());
+    if (c_only) {
+        if (out->scalars) CU_TRY(cudaMemcpyAsync(out->scalars, dscal, sizeof(double) * BP_NSCAL, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        return BP_OK;
+    }
+    if (out->S1) {
+        const Layout L{N, ldv, ldS, rowsS, (long long)rowsS * ldS, 2, 0};
+        if ((rc = emit_sym(h, dS, L, 1, out->S1))) return rc;
+        if (h->need_sync) { CU_TRY(cudaStreamSynchronize(st)); h->need_sync = false; }
+    }
+    const double inv_gamma = 1.0 / in->risk_aversion;
+    if (!in->jeffreys && in->w1) {
+        // injected posterior w: v1 = w1'S1w1 (:574), nu (:572-575), weights (:836)
+        launch_quadform(dS, ldS, dw1in, N, dscal + BP_SCAL_V1, n1, inv_gamma, dnu, dwts, st);
+        h->launches++;
+        CU_TRY(cudaMemcpyAsync(dw1, dw1in, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+    } else {
+        SolveParams sp{};
+        sp.n_windows = 1; sp.n_assets = N; sp.ldS = ldS; sp.win_stride = (long long)rowsS * ldS; sp.ldv = ldv;
+        sp.mode = in->jeffreys ? BP_MODE_JEFFREYS : BP_MODE_CONJUGATE;
+        sp.inv_gamma = inv_gamma;
+        sp.S = dS; sp.rhs = drhs; sp.scal = dscal; sp.w1 = dw1; sp.nu = dnu; sp.weights = dwts; sp.status = dstatus;
+        CU_TRY(launch_chol_solve(sp, h->sm_count, st));
+        h->launches++;
+    }
+    CU_TRY(cudaGetLastError());
+    if (out->scalars) CU_TRY(cudaMemcpyAsync(out->scalars, dscal, sizeof(double) * BP_NSCAL, cudaMemcpyDeviceToHost, st));
+    if (out->w1) CU_TRY(cudaMemcpyAsync(out->w1, dw1, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    if (out->nu) CU_TRY(cudaMemcpyAsync(out->nu, dnu, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    if (out->weights) CU_TRY(cudaMemcpyAsync(out->weights, dwts, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    if (out->status) CU_TRY(cudaMemcpyAsync(out->status, dstatus, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
     return BP_OK;
 }
 

@@ -21,6 +21,7 @@ enum {
     BP_S_M = 6,      // HF returns in the window
     BP_S_SUMA = 7,   // sum_k a_k
     BP_S_V1 = 8,     // w1' S1 w1                    (:574)
+    BP_S_MCM_AVG = 9,  // average MCM over the window (:112)
     BP_S_COUNT = 12
 };
 
@@ -36,6 +37,8 @@ struct PrepParams {
     const double* lr_hf;      // [R][ld] intraday log returns
     const double* caps;       // [D][ld]
     const double* mcm;        // [D]
+    int mcm_rows;             // observations averaged (min(n, available), :112)
+    const double* prior_n;    // [W] injected conjugate_prior_n (nullptr: from the MCM series)
     const double* rf_row;     // [D] risk-free forward-filled onto the daily rows
     const int* day_row;       // [W]
     const int* span_days;     // [W]
@@ -93,6 +96,26 @@ struct SolveParams {
     int* status;             // [W] 0 = ok, k+1 = non-positive pivot at column k
 };
 
+struct DenseParams {
+    int n_assets, ldS, ldv, n_window;
+    double n0, n1, c_in;
+    int has_c;
+    const double* T;       // [N][N] dense
+    const double* t;       // [N]
+    const double* S0;      // [N][N] dense
+    const double* w0;      // [N]
+    const double* S1_in;   // [N][N] dense or nullptr
+    double* s0w0;          // [N]
+    double* rhs;           // [ldv]
+    double* S_out;         // padded [rows][ldS]
+    double* scal;          // [BP_S_COUNT]
+};
+
+void launch_excess_returns(const double* lr, int ld, const double* rf_row, int day_row, int span_days, int n_window,
+                           int N, double* X, cudaStream_t st);
+void launch_dense_prep(const DenseParams& p, bool jeffreys, cudaStream_t st);
+void launch_quadform(const double* S, int ldS, const double* w, int N, double* v_out, double n1, double inv_gamma,
+                     double* nu, double* weights, cudaStream_t st);
 void launch_log_returns(const double* P, double* out, long long rows, int n_assets, int ld, int sm_count,
                         cudaStream_t st);
 size_t prep_smem_bytes(int n_window, int ldv);

@@ -173,14 +173,20 @@ __global__ void __launch_bounds__(PREP_THREADS) window_prep_kernel(PrepParams p)
     }
 
     // ---- MCM scaling (:90-114, :247-282): mean of the last n observations incl. d
-    const double* mcm = p.mcm;
-    double ms = 0.0;
-    for (int k = tid; k < p.n_window; k += PREP_THREADS) ms += mcm[day_row - p.n_window + 1 + k];
-    ms = block_sum(ms, scratch);
-    const double avg = ms / (double)p.n_window;
-    const double cur = mcm[day_row];
-    const double frac = cur > avg ? cur / avg : avg / cur;
-    const double n0 = (double)p.n_window * frac * p.mcm_scaling;
+    double avg = 0.0, n0;
+    if (p.prior_n) {
+        n0 = p.prior_n[w];                    // conjugate_prior_n= injection of the reference API
+    } else {
+        const double* mcm = p.mcm;
+        const int rows = p.mcm_rows;          // min(n, available observations): iloc[-n:] semantics (:112)
+        double ms = 0.0;
+        for (int k = tid; k < rows; k += PREP_THREADS) ms += mcm[day_row - rows + 1 + k];
+        ms = block_sum(ms, scratch);
+        avg = ms / (double)rows;
+        const double cur = mcm[day_row];
+        const double frac = cur > avg ? cur / avg : avg / cur;
+        n0 = (double)p.n_window * frac * p.mcm_scaling;
+    }
     const double n1 = n0 + (double)p.n_window;
 
     // ---- prior weights w0 (:679-701 value weighted, :661-677 equally weighted)
@@ -251,6 +257,7 @@ __global__ void __launch_bounds__(PREP_THREADS) window_prep_kernel(PrepParams p)
         scal[BP_S_V0] = v0;
         scal[BP_S_M] = (double)m;
         scal[BP_S_SUMA] = sa;
+        scal[BP_S_MCM_AVG] = avg;
     }
 }
 
@@ -309,6 +316,109 @@ void launch_unpack_vec(const double* v, int ldv, int N, long long W, double* out
     long long blocks = (total + 255) / 256;
     if (blocks > 4096) blocks = 4096;
     unpack_vec_kernel<<<(unsigned)blocks, 256, 0, st>>>(v, ldv, N, W, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// calculate_excess_log_returns_from_prices (:31-62) for ONE window: X[k][j] = L[r0+k][j] - a_k
+__global__ void excess_returns_kernel(const double* __restrict__ lr, int ld, const double* __restrict__ rf_row,
+                                      int day_row, int span_days, int n_window, int N, double* __restrict__ X) {
+    const int K = n_window - 1;
+    const long long r0 = (long long)day_row - K + 1;
+    const double expo = ((double)span_days / (double)K) / 365.0;
+    for (int k = blockIdx.x; k < K; k += gridDim.x) {
+        const double a = pow(1.0 + rf_row[r0 + k], expo) - 1.0;
+        for (int j = threadIdx.x; j < N; j += blockDim.x) X[(long long)k * N + j] = lr[(r0 + k) * ld + j] - a;
+    }
+}
+
+void launch_excess_returns(const double* lr, int ld, const double* rf_row, int day_row, int span_days, int n_window,
+                           int N, double* X, cudaStream_t st) {
+    int blocks = n_window - 1;
+    if (blocks > 1024) blocks = 1024;
+    excess_returns_kernel<<<blocks, 128, 0, st>>>(lr, ld, rf_row, day_row, span_days, n_window, N, X);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense single-window stages used when a posterior moment is injected through the reference's
+// optional arguments (conjugate_prior_S_df=, conjugate_c=, ... :382-577).  One CTA; N^2 work.
+//   s0w0 = S0 w0, v0 = w0'S0w0 (:78), c (:415-418) unless given, b = c s0w0 + t (:489),
+//   S1 = S0 + T (:358) unless given; S1 is written in the padded layout the solver expects.
+__global__ void __launch_bounds__(256) dense_conj_prep_kernel(DenseParams p) {
+    __shared__ double scratch[40];
+    const int N = p.n_assets, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double v0p = 0.0;
+    for (int i = warp; i < N; i += 8) {
+        double acc = 0.0;
+        for (int j = lane; j < N; j += 32) acc = fma(p.S0[(long long)i * N + j], p.w0[j], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            p.s0w0[i] = acc;
+            v0p = fma(p.w0[i], acc, v0p);
+        }
+    }
+    const double v0 = block_sum(v0p, scratch);
+    const double kk = p.n0 + (double)N + 2.0;
+    const double cc = p.has_c ? p.c_in : (2.0 * p.n0) / (kk + sqrt(kk * kk + 4.0 * p.n0 * v0));
+    if (p.T) {      // T == nullptr: only v0 and c are wanted
+        for (int i = tid; i < p.ldv; i += 256) p.rhs[i] = i < N ? fma(cc, p.s0w0[i], p.t[i]) : 0.0;
+        for (long long e = tid; e < (long long)N * N; e += 256) {
+            const int i = int(e / N), j = int(e - (long long)i * N);
+            const double v = p.S1_in ? p.S1_in[e] : p.S0[e] + p.T[e];
+            p.S_out[(long long)i * p.ldS + j] = v;
+        }
+    }
+    if (tid == 0) {
+        p.scal[BP_S_N0] = p.n0;
+        p.scal[BP_S_N1] = p.n1;
+        p.scal[BP_S_C] = cc;
+        p.scal[BP_S_V0] = v0;
+    }
+}
+
+// Jeffreys dense stage: J = T - (1/n) t t' (:600-601), rhs = t
+__global__ void __launch_bounds__(256) dense_jeffreys_prep_kernel(DenseParams p) {
+    const int N = p.n_assets, tid = threadIdx.x;
+    const double inv_n = 1.0 / (double)p.n_window;
+    for (int i = tid; i < p.ldv; i += 256) p.rhs[i] = i < N ? p.t[i] : 0.0;
+    for (long long e = tid; e < (long long)N * N; e += 256) {
+        const int i = int(e / N), j = int(e - (long long)i * N);
+        p.S_out[(long long)i * p.ldS + j] = p.T[e] - inv_n * p.t[i] * p.t[j];
+    }
+}
+
+// v = w'Sw for dense S (calculate_portfolio_variance, :64-88); optionally the posterior scalars for
+// an injected w1:  nu = (n1 + N + 2) w1 / (n1 - v)  (:572-575), weights = (1/gamma) nu (:836)
+__global__ void __launch_bounds__(256) quadform_kernel(const double* __restrict__ S, int ldS, const double* __restrict__ w,
+                                                       int N, double* v_out, double n1, double inv_gamma,
+                                                       double* nu, double* weights) {
+    __shared__ double scratch[40];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double part = 0.0;
+    for (int i = warp; i < N; i += 8) {
+        double acc = 0.0;
+        for (int j = lane; j < N; j += 32) acc = fma(S[(long long)i * ldS + j], w[j], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) part = fma(w[i], acc, part);
+    }
+    const double v = block_sum(part, scratch);
+    if (tid == 0) *v_out = v;
+    if (nu) {
+        const double mult = (n1 + (double)N + 2.0) / (n1 - v);
+        for (int i = tid; i < N; i += 256) {
+            nu[i] = w[i] * mult;
+            weights[i] = inv_gamma * (w[i] * mult);
+        }
+    }
+}
+
+void launch_dense_prep(const DenseParams& p, bool jeffreys, cudaStream_t st) {
+    if (jeffreys) dense_jeffreys_prep_kernel<<<1, 256, 0, st>>>(p);
+    else dense_conj_prep_kernel<<<1, 256, 0, st>>>(p);
+}
+
+void launch_quadform(const double* S, int ldS, const double* w, int N, double* v_out, double n1, double inv_gamma,
+                     double* nu, double* weights, cudaStream_t st) {
+    quadform_kernel<<<1, 256, 0, st>>>(S, ldS, w, N, v_out, n1, inv_gamma, nu, weights);
 }
 
 }  // namespace bp

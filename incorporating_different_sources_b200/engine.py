@@ -198,6 +198,14 @@ class BayesEngine:
         d.mcm_scaling = float(b.mcm_scaling)
         d.risk_aversion = float(b.risk_aversion)
         d.prior_weights = int(b.prior_weights)
+        d.mcm_rows = int(getattr(b, "mcm_rows", 0) or 0)
+        d.prior_n = None
+        if getattr(b, "prior_n", None) is not None:
+            pn = np.ascontiguousarray(b.prior_n, dtype=np.float64)
+            if pn.shape != (b.n_windows,):
+                raise ValueError("prior_n must have one entry per window")
+            keep.append(pn)
+            d.prior_n = pn.ctypes.data
         return d, keep
 
     def _alloc_outputs(self, W: int, names: Iterable[str], device_out: bool, into: Optional[dict]):
@@ -249,6 +257,15 @@ class BayesEngine:
         """``calculate_jeffreys_portfolio`` (:838-849) for every window of the batch."""
         return self._run(self._lib.bp_jeffreys_batched, batch, outputs, device_out, into, False)
 
+    def moments(self, batch: WindowBatch, outputs: Sequence[str], jeffreys: bool = False,
+                device_out: bool = False, into: Optional[dict] = None) -> Dict[str, object]:
+        """Posterior moments without the solve (t, w0, rhs, scalars, T, S0, S1)."""
+        lib = self._lib
+
+        def fn(h, d, o):
+            return lib.bp_moments_batched(h, d, 1 if jeffreys else 0, o)
+        return self._run(fn, batch, outputs, device_out, into, not jeffreys)
+
     def stats(self, batch: WindowBatch, want_T: bool = True):
         """``calculate_canonical_statistics_t`` / ``_T`` (:163-245)."""
         d, keep = self._batch_desc(batch, False)
@@ -272,6 +289,72 @@ class BayesEngine:
         if rc:
             _raise(rc)
         return n0, S0
+
+
+    # ------------------------------------------------------------------ single-window building blocks
+    def excess_returns(self, batch: WindowBatch) -> np.ndarray:
+        """``calculate_excess_log_returns_from_prices`` (:31-62) of a one-window batch."""
+        d, keep = self._batch_desc(batch, False)
+        X = np.empty((batch.rolling_window - 1, self.n_assets))
+        rc = self._lib.bp_excess_returns(self._h, C.byref(d), X.ctypes.data)
+        del keep
+        if rc:
+            _raise(rc)
+        return X
+
+    def quadratic_form(self, w: np.ndarray, S: np.ndarray) -> float:
+        """``calculate_portfolio_variance`` (:64-88): w'Sw."""
+        w = _c64(w)
+        S = _c64(S)
+        out = np.empty(1)
+        rc = self._lib.bp_quadratic_form(self._h, int(w.shape[0]), w.ctypes.data, S.ctypes.data, out.ctypes.data)
+        if rc:
+            _raise(rc)
+        return float(out[0])
+
+    def dense_posterior(self, *, jeffreys: bool, rolling_window: int, risk_aversion: float, T, t, S0=None, w0=None,
+                        n0: float = 0.0, n1=None, c=None, S1=None, w1=None) -> Dict[str, object]:
+        """Posterior from dense (possibly injected) moments: the optional-argument forms of :382-608."""
+        keep = []
+        pr = _lib.DenseProblem()
+        if T is None:
+            N = int(np.asarray(w0).shape[0])
+            pr.T = pr.t = None
+        else:
+            T = _c64(T)
+            t = _c64(t)
+            N = T.shape[0]
+            keep += [T, t]
+            pr.T, pr.t = T.ctypes.data, t.ctypes.data
+        pr.n_assets, pr.jeffreys, pr.rolling_window = N, int(bool(jeffreys)), int(rolling_window)
+        pr.risk_aversion = float(risk_aversion)
+        pr.n0 = float(n0)
+        for name, val, shape in (("S0", S0, (N, N)), ("w0", w0, (N,)), ("S1", S1, (N, N)), ("w1", w1, (N,))):
+            if val is None:
+                setattr(pr, name, None)
+                continue
+            a = _c64(val)
+            if a.shape != shape:
+                raise ValueError(f"{name} has shape {a.shape}, expected {shape}")
+            keep.append(a)
+            setattr(pr, name, a.ctypes.data)
+        for name, val in (("n1", n1), ("c", c)):
+            if val is None:
+                setattr(pr, name, None)
+            else:
+                a = np.array([float(val)])
+                keep.append(a)
+                setattr(pr, name, a.ctypes.data)
+        res = {"scalars": np.zeros(BP_NSCAL), "S1": np.empty((N, N)), "w1": np.empty(N), "nu": np.empty(N),
+               "weights": np.empty(N), "status": np.zeros(1, dtype=np.int32)}
+        out = _lib.DenseResult()
+        for k, v in res.items():
+            setattr(out, k, v.ctypes.data)
+        rc = self._lib.bp_dense_posterior(self._h, C.byref(pr), C.byref(out))
+        del keep
+        if rc:
+            _raise(rc)
+        return res
 
 
 def scalars_to_dict(scal_row: np.ndarray) -> Dict[str, float]:

@@ -29,6 +29,8 @@ class WindowBatch:
     mcm_scaling: float = 1.0
     risk_aversion: float = 1.0
     prior_weights: int = 0       # 0 value weighted, 1 equally weighted
+    mcm_rows: int = 0            # MCM observations averaged (0 = rolling_window)
+    prior_n: Optional[np.ndarray] = None   # injected conjugate_prior_n per window
 
     @property
     def n_windows(self) -> int:
