@@ -125,6 +125,10 @@ int bp_get_stage_times(bp_handle* h, double* ms /*[BP_NSTAGE]*/, long long* laun
 /* Host -> HBM: replaces the pandas frames of get_market_data() (data_handling.py:270-291).  Also
  * computes both log-return matrices on the device (:37, :314). */
 int bp_upload_market(bp_handle* h, const bp_market_desc* m);
+/* Same, but returns as soon as the copies are queued: the host arrays must be page-locked and stay
+ * valid until bp_synchronize().  The intraday block travels on a second stream, so a following
+ * bp_jeffreys_batched / bp_stats_batched overlaps the transfer; conjugate calls wait for it. */
+int bp_upload_market_async(bp_handle* h, const bp_market_desc* m);
 /* Re-run the log-return stage on the resident prices (device-only timing of the whole path). */
 int bp_prepare_market(bp_handle* h);
 

@@ -23,6 +23,7 @@ EXPORTED = [
     "bp_prepare_market", "bp_stats_batched", "bp_hf_cov_batched", "bp_conjugate_batched",
     "bp_jeffreys_batched", "bp_set_stage_timing", "bp_get_stage_times",
     "bp_excess_returns", "bp_quadratic_form", "bp_dense_posterior", "bp_moments_batched",
+    "bp_upload_market_async",
 ]
 BP_NSTAGE = 8
 STAGES = ("logret", "prep", "gram", "solve")
@@ -93,6 +94,7 @@ def load():
     lib.bp_launch_count.argtypes = [C.c_void_p]
     lib.bp_launch_count.restype = C.c_longlong
     lib.bp_upload_market.argtypes = [C.c_void_p, C.POINTER(MarketDesc)]
+    lib.bp_upload_market_async.argtypes = [C.c_void_p, C.POINTER(MarketDesc)]
     lib.bp_prepare_market.argtypes = [C.c_void_p]
     lib.bp_stats_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.c_void_p, C.c_void_p]
     lib.bp_hf_cov_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.c_void_p, C.c_void_p]

@@ -62,8 +62,14 @@ struct bp_handle {
     bool has_market = false;
     int N = 0, D = 0, ld = 0, n_mcm = 0;
     long long R = 0;
+    // prices / caps / hf_prices keep the caller's dense [rows][N] layout; lr_d / lr_hf are padded to ld
     double *prices = nullptr, *lr_d = nullptr, *caps = nullptr, *hf_prices = nullptr, *lr_hf = nullptr,
            *mcm = nullptr, *rf_row = nullptr;
+    bool has_caps = false;
+    size_t cap_daily = 0, cap_hf = 0, cap_mcm = 0, cap_days = 0;   // allocated sizes (elements) for buffer reuse
+    cudaStream_t copy_stream = nullptr;                  // intraday H2D + its log-return kernel
+    cudaEvent_t ev_main = nullptr, ev_hf = nullptr;
+    bool hf_pending = false;
     CUtensorMap map_d, map_hf;
     // window descriptors on the device: day_row, span, row0, hf_row0, hf_m
     int* desc = nullptr;
@@ -115,7 +121,17 @@ void free_market(bp_handle* h) {
     cudaFree(h->prices); cudaFree(h->lr_d); cudaFree(h->caps); cudaFree(h->hf_prices);
     cudaFree(h->lr_hf); cudaFree(h->mcm); cudaFree(h->rf_row);
     h->prices = h->lr_d = h->caps = h->hf_prices = h->lr_hf = h->mcm = h->rf_row = nullptr;
+    h->cap_daily = h->cap_hf = h->cap_mcm = h->cap_days = 0;
     h->has_market = false;
+}
+
+// conjugate stages read lr_hf, produced on the copy stream: order the compute stream after it
+int wait_hf(bp_handle* h) {
+    if (h->hf_pending) {
+        CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_hf, 0));
+        h->hf_pending = false;
+    }
+    return BP_OK;
 }
 
 int make_map(bp_handle* h, CUtensorMap* map, const double* base, long long rows, int ld) {
@@ -219,7 +235,7 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         if (!b->prior_n && (b->mcm_index < 0 || b->mcm_index >= h->n_mcm))
             return fail(BP_ERR_INVALID, "mcm_index %d out of range", b->mcm_index);
         if (b->mcm_rows < 0 || b->mcm_rows > n) return fail(BP_ERR_INVALID, "mcm_rows must be in [0, rolling_window]");
-        if (b->prior_weights == 0 && !h->caps) return fail(BP_ERR_STATE, "value-weighted prior needs market caps");
+        if (b->prior_weights == 0 && !h->has_caps) return fail(BP_ERR_STATE, "value-weighted prior needs market caps");
     }
     std::vector<int> host((size_t)5 * W, 0);
     int max_m = 0;
@@ -339,7 +355,8 @@ PrepParams prep_params(const bp_handle* h, const bp_window_batch* b, const Batch
     p.mcm_scaling = b->mcm_scaling;
     p.lr_daily = h->lr_d;
     p.lr_hf = h->lr_hf;
-    p.caps = h->caps;
+    p.caps = h->has_caps ? h->caps : nullptr;
+    p.ld_caps = h->N;
     p.mcm = (mode == BP_MODE_CONJUGATE && h->mcm) ? h->mcm + (size_t)b->mcm_index * h->D : nullptr;
     p.mcm_rows = B.mcm_rows;
     p.prior_n = B.prior_n ? B.prior_n + w0 : nullptr;
@@ -410,6 +427,7 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
     int rc = upload_batch(h, b, mode == BP_MODE_CONJUGATE, &B);
     if (rc) return rc;
     CU_TRY(cudaSetDevice(h->device));
+    if (mode == BP_MODE_CONJUGATE && (rc = wait_hf(h))) return rc;
     const Layout L = make_layout(h, B.max_m);
     int Wc = (int)std::min<size_t>((size_t)B.W, std::max<size_t>(1, h->ws_limit / L.per_window));
     rc = ensure_ws(h, (size_t)Wc * L.per_window + 256);
@@ -520,6 +538,12 @@ int bp_init(int device, bp_handle** out) {
         return fail(BP_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
     }
     h->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_hf, cudaEventDisableTiming) != cudaSuccess) {
+        delete h;
+        return fail(BP_ERR_CUDA, "could not create the copy stream / events");
+    }
     *out = h;
     return BP_OK;
 }
@@ -528,7 +552,11 @@ int bp_destroy(bp_handle* h) {
     if (!h) return BP_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->copy_stream);
     free_market(h);
+    cudaStreamDestroy(h->copy_stream);
+    cudaEventDestroy(h->ev_main);
+    cudaEventDestroy(h->ev_hf);
     cudaFree(h->desc);
     cudaFree(h->prior_n);
     cudaFree(h->ws);
@@ -546,6 +574,7 @@ int bp_set_stream(bp_handle* h, void* cuda_stream) {
 
 int bp_synchronize(bp_handle* h) {
     if (!h) return fail(BP_ERR_INVALID, "null handle");
+    CU_TRY(cudaStreamSynchronize(h->copy_stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
     return BP_OK;
 }
@@ -597,12 +626,14 @@ int bp_prepare_market(bp_handle* h) {
     if (!h) return fail(BP_ERR_INVALID, "null handle");
     if (!h->has_market) return fail(BP_ERR_STATE, "no market uploaded");
     CU_TRY(cudaSetDevice(h->device));
+    int rc = wait_hf(h);
+    if (rc) return rc;
     {
         StageTimer tm(h, BP_STAGE_LOGRET);
-        launch_log_returns(h->prices, h->lr_d, h->D, h->N, h->ld, h->sm_count, h->stream);
+        launch_log_returns(h->prices, h->N, h->lr_d, h->ld, h->D, h->N, h->sm_count, h->stream);
         h->launches++;
         if (h->R > 0) {
-            launch_log_returns(h->hf_prices, h->lr_hf, h->R, h->N, h->ld, h->sm_count, h->stream);
+            launch_log_returns(h->hf_prices, h->N, h->lr_hf, h->ld, h->R, h->N, h->sm_count, h->stream);
             h->launches++;
         }
     }
@@ -610,7 +641,12 @@ int bp_prepare_market(bp_handle* h) {
     return BP_OK;
 }
 
-int bp_upload_market(bp_handle* h, const bp_market_desc* m) {
+// Shared body of bp_upload_market / bp_upload_market_async.  Device buffers are reused when the new
+// market fits the allocated capacity; the host arrays are copied in their dense layout with plain 1-D
+// copies (full PCIe rate from pinned memory) and padded on the fly by the log-return kernel.  The
+// intraday block (by far the largest) goes over a second stream together with its log-return kernel,
+// so stages that do not read it (Jeffreys, daily statistics) overlap the transfer.
+static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocking) {
     if (!h || !m) return fail(BP_ERR_INVALID, "null handle or market");
     if (m->n_assets <= 0 || m->n_days < 2 || !m->prices || !m->rf_row)
         return fail(BP_ERR_INVALID, "market needs n_assets > 0, n_days >= 2, prices and rf_row");
@@ -618,33 +654,50 @@ int bp_upload_market(bp_handle* h, const bp_market_desc* m) {
     if (m->n_hf_rows > 0x7fffffffLL) return fail(BP_ERR_INVALID, "too many intraday rows for int32 row indices");
     if (m->n_mcm < 0 || (m->n_mcm > 0 && !m->mcm)) return fail(BP_ERR_INVALID, "mcm missing");
     CU_TRY(cudaSetDevice(h->device));
-    CU_TRY(cudaStreamSynchronize(h->stream));
-    free_market(h);
     const int N = m->n_assets, D = m->n_days, ld = round_up(N, 16);
     const long long R = m->n_hf_rows;
+    const size_t need_daily = (size_t)D * ld, need_hf = (size_t)R * ld, need_mcm = (size_t)std::max(m->n_mcm, 1) * D;
+    if (need_daily > h->cap_daily || need_hf > h->cap_hf || need_mcm > h->cap_mcm || (size_t)D > h->cap_days) {
+        // grow: everything in flight must be done with the old buffers
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        CU_TRY(cudaStreamSynchronize(h->copy_stream));
+        free_market(h);
+        CU_TRY(cudaMalloc(&h->prices, sizeof(double) * need_daily));
+        CU_TRY(cudaMalloc(&h->lr_d, sizeof(double) * need_daily));
+        CU_TRY(cudaMalloc(&h->caps, sizeof(double) * need_daily));
+        CU_TRY(cudaMalloc(&h->rf_row, sizeof(double) * (size_t)D));
+        CU_TRY(cudaMalloc(&h->mcm, sizeof(double) * need_mcm));
+        if (need_hf) {
+            CU_TRY(cudaMalloc(&h->hf_prices, sizeof(double) * need_hf));
+            CU_TRY(cudaMalloc(&h->lr_hf, sizeof(double) * need_hf));
+        }
+        h->cap_daily = need_daily;
+        h->cap_hf = need_hf;
+        h->cap_mcm = need_mcm;
+        h->cap_days = (size_t)D;
+    }
     h->N = N; h->D = D; h->ld = ld; h->R = R; h->n_mcm = m->n_mcm;
-    const size_t drow = sizeof(double) * (size_t)ld, srow = sizeof(double) * (size_t)N;
-    auto upload2d = [&](double** dst, const double* src, long long rows) -> int {
-        CU_TRY(cudaMalloc(dst, drow * (size_t)rows));
-        if (ld > N)
-            CU_TRY(cudaMemset2DAsync(*dst + N, drow, 0, drow - srow, (size_t)rows, h->stream));
-        CU_TRY(cudaMemcpy2DAsync(*dst, drow, src, srow, srow, (size_t)rows, cudaMemcpyHostToDevice, h->stream));
-        return BP_OK;
-    };
+    h->has_caps = m->caps != nullptr;
+    cudaStream_t st = h->stream;
+    // the copy stream must not overwrite buffers that earlier launches on the compute stream still read
+    CU_TRY(cudaEventRecord(h->ev_main, st));
+    CU_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_main, 0));
     int rc;
-    if ((rc = upload2d(&h->prices, m->prices, D))) return rc;
-    CU_TRY(cudaMalloc(&h->lr_d, drow * (size_t)D));
-    if (m->caps && (rc = upload2d(&h->caps, m->caps, D))) return rc;
     if (R > 0) {
-        if ((rc = upload2d(&h->hf_prices, m->hf_prices, R))) return rc;
-        CU_TRY(cudaMalloc(&h->lr_hf, drow * (size_t)R));
+        CU_TRY(cudaMemcpyAsync(h->hf_prices, m->hf_prices, sizeof(double) * (size_t)R * N, cudaMemcpyHostToDevice, h->copy_stream));
+        launch_log_returns(h->hf_prices, N, h->lr_hf, ld, R, N, h->sm_count, h->copy_stream);
+        h->launches++;
+        CU_TRY(cudaEventRecord(h->ev_hf, h->copy_stream));
+        h->hf_pending = true;
     }
-    if (m->n_mcm > 0) {
-        CU_TRY(cudaMalloc(&h->mcm, sizeof(double) * (size_t)m->n_mcm * D));
-        CU_TRY(cudaMemcpyAsync(h->mcm, m->mcm, sizeof(double) * (size_t)m->n_mcm * D, cudaMemcpyHostToDevice, h->stream));
-    }
-    CU_TRY(cudaMalloc(&h->rf_row, sizeof(double) * (size_t)D));
-    CU_TRY(cudaMemcpyAsync(h->rf_row, m->rf_row, sizeof(double) * (size_t)D, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->prices, m->prices, sizeof(double) * (size_t)D * N, cudaMemcpyHostToDevice, st));
+    if (m->caps) CU_TRY(cudaMemcpyAsync(h->caps, m->caps, sizeof(double) * (size_t)D * N, cudaMemcpyHostToDevice, st));
+    if (m->n_mcm > 0)
+        CU_TRY(cudaMemcpyAsync(h->mcm, m->mcm, sizeof(double) * (size_t)m->n_mcm * D, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(h->rf_row, m->rf_row, sizeof(double) * (size_t)D, cudaMemcpyHostToDevice, st));
+    launch_log_returns(h->prices, N, h->lr_d, ld, D, N, h->sm_count, st);
+    h->launches++;
+    CU_TRY(cudaGetLastError());
     if ((rc = make_map(h, &h->map_d, h->lr_d, D, ld))) return rc;
     if (R > 0) {
         if ((rc = make_map(h, &h->map_hf, h->lr_hf, R, ld))) return rc;
@@ -652,12 +705,17 @@ int bp_upload_market(bp_handle* h, const bp_market_desc* m) {
         h->map_hf = h->map_d;
     }
     h->has_market = true;
-    rc = bp_prepare_market(h);
-    if (rc) return rc;
-    // the caller's host arrays may be pageable and may be freed after return
-    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (blocking) {
+        // the caller's host arrays may be pageable and may be freed after return
+        CU_TRY(cudaStreamSynchronize(h->copy_stream));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
     return BP_OK;
 }
+
+int bp_upload_market(bp_handle* h, const bp_market_desc* m) { return upload_market_impl(h, m, true); }
+
+int bp_upload_market_async(bp_handle* h, const bp_market_desc* m) { return upload_market_impl(h, m, false); }
 
 int bp_conjugate_batched(bp_handle* h, const bp_window_batch* b, const bp_outputs* out) {
     if (!out) return fail(BP_ERR_INVALID, "outputs missing");

@@ -11,24 +11,25 @@
 // [rows][ldS] device layout produced by the Gram kernel (lower triangle):
 //   U  panel update   C = S[j0:, j0:j0+32] - L[j0:, :j0] L[j0:j0+32, :j0]'     DMMA, fragments read
 //                     straight from global/L2 as 32-byte vectors (k-permuted, see below)
-//   F  diagonal block 32x32 Cholesky + triangular inverse by one warp (row in registers,
-//                     broadcasts through shared memory, warp shuffles for the pivot)
-//   T  panel solve    L[j0+32:, j0:j0+32] = C * inv(L_d)'                       DMMA
+//   F  diagonal block 32x32 right-looking Cholesky by one warp (row in registers, warp shuffles,
+//                     rsqrt pivots: the dependent FP64 chain per column is 4 operations)
+//   T  panel solve    L[j0+32:, j0:j0+32] = C * inv(L_d)', one thread per row, L_d broadcast
+//                     from shared memory (same FP64 rate as DMMA on B200, no triangular inverse)
 // The right-hand side rides along as one extra row (row Nr = roundup(N,32)) of the matrix, so the
 // forward substitution L z = b is a by-product of the factorisation.  The back substitution then
 // walks the panels in reverse with coalesced row reads and a warp-level triangular solve.
 //
-// k-permutation: a lane (g, tig) loads the four consecutive doubles k0+4*tig .. k0+4*tig+3 of its
-// row; DMMA step q (0..3) contracts the k-set {k0 + 4*tig + q}.  A and B fragments use the same
-// assignment, so the contraction over the 16-wide chunk is exact while every global load is a
-// full 32-byte sector.
+// k-permutation: of every 16-wide k chunk a lane (g, tig) loads columns {2tig, 2tig+1, 8+2tig,
+// 9+2tig} of its row (two 16-byte loads; a warp-wide load covers whole 32-byte sectors); DMMA step
+// q (0..3) contracts the q-th of those four columns over the four tig lanes.  A and B fragments use
+// the same assignment, so the contraction over the chunk is exact.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace bp {
 
-constexpr int CH_THREADS = 256;
-constexpr int CH_WARPS = CH_THREADS / 32;
 constexpr int NB = 32;
 constexpr int LDP = 33;    // padded shared-memory row stride of the 32x32 blocks
 
@@ -36,65 +37,55 @@ struct d4 {
     double v[4];
 };
 
+// ptr addresses column k0 + 2*tig of the lane's row: the lane takes columns {2tig, 2tig+1, 8+2tig, 9+2tig}
+// of the 16-wide chunk, so each of the two 16-byte loads of a warp covers whole 32-byte sectors
 __device__ __forceinline__ d4 load4(const double* ptr, bool pred) {
     d4 r;
     if (pred) {
         const double2 lo = *reinterpret_cast<const double2*>(ptr);
-        const double2 hi = *reinterpret_cast<const double2*>(ptr + 2);
+        const double2 hi = *reinterpret_cast<const double2*>(ptr + 8);
         r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = hi.x; r.v[3] = hi.y;
     } else {
         r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0.0;
     }
     return r;
 }
-// as load4, but elements at index >= nvalid (columns beyond N, never written) read as zero
-__device__ __forceinline__ d4 load4_bounded(const double* ptr, bool pred, int nvalid) {
-    d4 r = load4(ptr, pred && nvalid > 0);
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-        if (e >= nvalid) r.v[e] = 0.0;
-    return r;
-}
-
-// 32x32 Cholesky of the block in Ld (stride LDP) by one warp; writes L (upper part zeroed) back to
-// Ld and inv(L) to Li.  Returns the 1-based index of the first non-positive pivot, or 0.
-__device__ int potrf_trtri_warp(double* Ld, double* Li, int lane) {
+// 32x32 Cholesky of the block in Ld (stride LDP) by one warp, right-looking, row `lane` in registers.
+// The FP64 pipe is shared with the DMMAs of the co-resident CTA, so what matters is the length of
+// the dependent FP64 chain: per column it is one shuffle, one rsqrt (no sqrt + divide), one multiply
+// and one FMA; the 496 trailing updates are independent.  Writes L (upper part zeroed) back to Ld and
+// the reciprocal diagonal to invd.  Returns the 1-based index of the first non-positive pivot, or 0.
+__device__ int potrf_warp(double* Ld, double* invd, int lane) {
     double r[NB];
 #pragma unroll
     for (int k = 0; k < NB; ++k) r[k] = Ld[lane * LDP + k];
     int fail = 0;
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
-        double s = r[k];
-#pragma unroll
-        for (int q = 0; q < k; ++q) s = fma(-r[q], Ld[k * LDP + q], s);
-        const double piv = __shfl_sync(0xffffffffu, s, k);
+        const double piv = __shfl_sync(0xffffffffu, r[k], k);
         if (!(piv > 0.0) && fail == 0) fail = k + 1;
-        const double lkk = sqrt(piv);
-        const double inv = 1.0 / lkk;
-        r[k] = lane == k ? lkk : (lane > k ? s * inv : 0.0);
-        Ld[lane * LDP + k] = r[k];
-        __syncwarp();
-    }
-    // inverse of the lower-triangular block: lane j owns column j of X = inv(L)
-    double x[NB];
+        const double inv = rsqrt(piv);
+        const double l = lane > k ? r[k] * inv : (lane == k ? piv * inv : 0.0);
+        r[k] = l;
+        if (lane == k) invd[k] = inv;
 #pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        double s = lane == i ? 1.0 : 0.0;
-#pragma unroll
-        for (int q = 0; q < i; ++q) s = fma(-Ld[i * LDP + q], x[q], s);
-        x[i] = i < lane ? 0.0 : s / Ld[i * LDP + i];
+        for (int j = k + 1; j < NB; ++j) {
+            const double lj = __shfl_sync(0xffffffffu, l, j);
+            r[j] = fma(-l, lj, r[j]);
+        }
     }
 #pragma unroll
-    for (int i = 0; i < NB; ++i) Li[i * LDP + lane] = x[i];
+    for (int k = 0; k < NB; ++k) Ld[lane * LDP + k] = k <= lane ? r[k] : 0.0;
     return fail;
 }
 
-__global__ void __launch_bounds__(CH_THREADS, 2) chol_solve_kernel(SolveParams p) {
+template <int CH_WARPS>
+__global__ void __launch_bounds__(CH_WARPS * 32, 16 / CH_WARPS) chol_solve_kernel(SolveParams p) {
+    constexpr int CH_THREADS = CH_WARPS * 32;
     extern __shared__ double sm[];
     double* Ld = sm;                       // [32][33]
-    double* Li = Ld + NB * LDP;            // [32][33]
-    double* red = Li + NB * LDP;           // [CH_WARPS][32]
+    double* invd = Ld + NB * LDP;          // [32] reciprocal diagonal of the current block (+ padding)
+    double* red = invd + NB * LDP;         // [CH_WARPS][32]
     double* scratch = red + CH_WARPS * NB; // [40]
     double* xs = scratch + 40;             // [Nr]
     __shared__ int fail_s;
@@ -123,29 +114,34 @@ __global__ void __launch_bounds__(CH_THREADS, 2) chol_solve_kernel(SolveParams p
                     for (int nt = 0; nt < 4; ++nt) acc[i][nt][0] = acc[i][nt][1] = 0.0;
                 int rowA[4];
                 bool realA[4];
+                int ni = 0;                  // m-tiles this warp really has in this pass (warp-uniform)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int q = qb + i * CH_WARPS;
                     rowA[i] = j0 + 8 * q + g;
                     realA[i] = q < mt_total && (rowA[i] < N || rowA[i] == Nr);
+                    ni += q < mt_total ? 1 : 0;
                 }
                 for (int k0 = 0; k0 < j0; k0 += 16) {
                     d4 a[4], b[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        a[i] = load4(S + (long long)rowA[i] * ld + k0 + 4 * tig, realA[i]);
+                        a[i] = load4(S + (long long)rowA[i] * ld + k0 + 2 * tig, realA[i]);
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt) {
                         const int rb = j0 + 8 * nt + g;
-                        b[nt] = load4(S + (long long)rb * ld + k0 + 4 * tig, rb < N);
+                        b[nt] = load4(S + (long long)rb * ld + k0 + 2 * tig, rb < N);
                     }
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq)
+                    for (int i = 0; i < 4; ++i) {
+                        if (i < ni) {        // skip the DMMAs of m-tile slots past the end of the panel
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
+                            for (int qq = 0; qq < 4; ++qq)
 #pragma unroll
-                            for (int nt = 0; nt < 4; ++nt)
-                                dmma884(acc[i][nt][0], acc[i][nt][1], a[i].v[qq], b[nt].v[qq]);
+                                for (int nt = 0; nt < 4; ++nt)
+                                    dmma884(acc[i][nt][0], acc[i][nt][1], a[i].v[qq], b[nt].v[qq]);
+                        }
+                    }
                 }
                 // C = S - acc, masked for padding; diagonal-block tiles go to shared memory
 #pragma unroll
@@ -180,7 +176,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) chol_solve_kernel(SolveParams p
             __syncthreads();
             // ---------------- F: diagonal block
             if (warp == 0) {
-                const int f = potrf_trtri_warp(Ld, Li, lane);
+                const int f = potrf_warp(Ld, invd, lane);
                 if (lane == 0 && f != 0 && fail_s == 0) fail_s = j0 + f;
             }
             __syncthreads();
@@ -189,34 +185,31 @@ __global__ void __launch_bounds__(CH_THREADS, 2) chol_solve_kernel(SolveParams p
                 const int row = j0 + i, col = j0 + lane;
                 if (row < N && col < N && lane <= i) S[(long long)row * ld + col] = Ld[i * LDP + lane];
             }
-            // ---------------- T: rows below the diagonal block:  X = C * inv(L_d)'
-            for (int qb = warp; qb < mt_total; qb += CH_WARPS) {
-                if (qb < NB / 8) continue;      // the diagonal block itself
-                const int row = j0 + 8 * qb + g;
-                const bool real = row < N || row == Nr;
-                double acc[4][2];
+            // ---------------- T: rows below the diagonal block (and the right-hand-side row):
+            // x L_d' = c, one thread per row, right-looking so that the 496 updates are independent
+            {
+                const int nbelow = N - (j0 + NB) > 0 ? N - (j0 + NB) : 0;
+                for (int e = tid; e < nbelow + 1; e += CH_THREADS) {
+                    const int row = e < nbelow ? j0 + NB + e : Nr;
+                    double* prow = S + (long long)row * ld + j0;
+                    double pv[NB];
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
-#pragma unroll
-                for (int kc = 0; kc < 2; ++kc) {
-                    const int c0 = j0 + 16 * kc + 4 * tig;
-                    const d4 a = load4_bounded(S + (long long)row * ld + c0, real, N - c0);
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        const int k = 16 * kc + 4 * tig + qq;
-#pragma unroll
-                        for (int nt = 0; nt < 4; ++nt)
-                            dmma884(acc[nt][0], acc[nt][1], a.v[qq], Li[(8 * nt + g) * LDP + k]);
+                    for (int c = 0; c < NB; c += 2) {
+                        double2 v = make_double2(0.0, 0.0);
+                        if (j0 + c < N) v = *reinterpret_cast<const double2*>(prow + c);
+                        pv[c] = v.x;
+                        pv[c + 1] = v.y;
                     }
-                }
-                __syncwarp();   // all lanes have read the C tile before it is overwritten
-                if (real) {
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) {
-                        const int col = j0 + 8 * nt + 2 * tig;
-                        if (col < N)
-                            *reinterpret_cast<double2*>(S + (long long)row * ld + col) = make_double2(acc[nt][0], acc[nt][1]);
+                    for (int c = 0; c < NB; ++c) {
+                        const double x = pv[c] * invd[c];
+                        pv[c] = x;
+#pragma unroll
+                        for (int j = c + 1; j < NB; ++j) pv[j] = fma(-x, Ld[j * LDP + c], pv[j]);
                     }
+#pragma unroll
+                    for (int c = 0; c < NB; c += 2)
+                        if (j0 + c < N) *reinterpret_cast<double2*>(prow + c) = make_double2(pv[c], pv[c + 1]);
                 }
             }
             __syncthreads();
@@ -251,9 +244,10 @@ __global__ void __launch_bounds__(CH_THREADS, 2) chol_solve_kernel(SolveParams p
                 double r = xs[col];
 #pragma unroll
                 for (int wv = 0; wv < CH_WARPS; ++wv) r -= red[wv * NB + lane];
+                const double rd = 1.0 / Ld[lane * LDP + lane];      // all 32 reciprocals in parallel
 #pragma unroll
                 for (int k = NB - 1; k >= 0; --k) {
-                    const double xk = __shfl_sync(0xffffffffu, r, k) / Ld[k * LDP + k];
+                    const double xk = __shfl_sync(0xffffffffu, r * rd, k);
                     if (lane == k) r = xk;
                     if (lane < k) r = fma(-Ld[k * LDP + lane], xk, r);
                 }
@@ -284,16 +278,28 @@ __global__ void __launch_bounds__(CH_THREADS, 2) chol_solve_kernel(SolveParams p
     }
 }
 
-cudaError_t launch_chol_solve(const SolveParams& p, int sm_count, cudaStream_t st) {
-    if (p.n_windows <= 0) return cudaSuccess;
+template <int CH_WARPS>
+static cudaError_t launch_chol_t(const SolveParams& p, int sm_count, cudaStream_t st) {
     const int Nr = (p.n_assets + NB - 1) / NB * NB;
     const size_t smem = sizeof(double) * (size_t)(2 * NB * LDP + CH_WARPS * NB + 40 + Nr);
-    cudaError_t e = cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(chol_solve_kernel<CH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int grid = 2 * sm_count;
+    int grid = (16 / CH_WARPS) * sm_count;
     if (grid > p.n_windows) grid = p.n_windows;
-    chol_solve_kernel<<<grid, CH_THREADS, smem, st>>>(p);
+    chol_solve_kernel<CH_WARPS><<<grid, CH_WARPS * 32, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t launch_chol_solve(const SolveParams& p, int sm_count, cudaStream_t st) {
+    if (p.n_windows <= 0) return cudaSuccess;
+    static int warps = [] {
+        const char* e = getenv("BP_CHOL_WARPS");      // tuning knob: warps per window (CTA), 16/warps CTAs per SM
+        const int v = e ? atoi(e) : 4;
+        return (v == 2 || v == 4 || v == 8) ? v : 4;
+    }();
+    if (warps == 2) return launch_chol_t<2>(p, sm_count, st);
+    if (warps == 4) return launch_chol_t<4>(p, sm_count, st);
+    return launch_chol_t<8>(p, sm_count, st);
 }
 
 }  // namespace bp

@@ -35,7 +35,8 @@ struct PrepParams {
     double mcm_scaling;
     const double* lr_daily;   // [D][ld] daily log returns (row r = log(P_r / P_{r-1}))
     const double* lr_hf;      // [R][ld] intraday log returns
-    const double* caps;       // [D][ld]
+    const double* caps;       // [D][ld_caps] (dense upload layout)
+    int ld_caps;
     const double* mcm;        // [D]
     int mcm_rows;             // observations averaged (min(n, available), :112)
     const double* prior_n;    // [W] injected conjugate_prior_n (nullptr: from the MCM series)
@@ -116,8 +117,8 @@ void launch_excess_returns(const double* lr, int ld, const double* rf_row, int d
 void launch_dense_prep(const DenseParams& p, bool jeffreys, cudaStream_t st);
 void launch_quadform(const double* S, int ldS, const double* w, int N, double* v_out, double n1, double inv_gamma,
                      double* nu, double* weights, cudaStream_t st);
-void launch_log_returns(const double* P, double* out, long long rows, int n_assets, int ld, int sm_count,
-                        cudaStream_t st);
+void launch_log_returns(const double* P, int ld_in, double* out, int ld_out, long long rows, int n_assets,
+                        int sm_count, cudaStream_t st);
 size_t prep_smem_bytes(int n_window, int ldv);
 cudaError_t launch_window_prep(const PrepParams& p, int n_windows, cudaStream_t st);
 void launch_unpack_sym(const double* S, long long win_stride, int ldS, int N, int W, double* out, cudaStream_t st);

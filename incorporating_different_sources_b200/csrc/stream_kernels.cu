@@ -20,34 +20,48 @@
 namespace bp {
 
 // ------------------------------------------------------------------------------------------------
-__global__ void log_returns_kernel(const double* __restrict__ P, double* __restrict__ out, long long rows,
-                                   int n_assets, int ld) {
-    const long long half = ld >> 1;
-    const long long total = rows * half;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / half;
-        const int c = int(i - r * half) * 2;
+// P is the DENSE host layout [rows][ld_in = n_assets]; out is padded to ld_out (multiple of 16, the
+// TMA / vector-load layout), pad columns are written as zero.  One thread per pair of columns.
+template <bool VEC>
+__global__ void log_returns_kernel(const double* __restrict__ P, int ld_in, double* __restrict__ out, int ld_out,
+                                   long long rows, int n_assets) {
+    const int half = ld_out >> 1;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (c >= ld_out) return;
+    for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
         double2 o = make_double2(0.0, 0.0);
-        if (r > 0) {
-            const double2 p = *reinterpret_cast<const double2*>(P + r * ld + c);
-            const double2 q = *reinterpret_cast<const double2*>(P + (r - 1) * ld + c);
-            if (c < n_assets) o.x = log(p.x / q.x);
-            if (c + 1 < n_assets) o.y = log(p.y / q.y);
+        if (r > 0 && c < n_assets) {
+            const double* cur = P + r * ld_in + c;
+            const double* prv = cur - ld_in;
+            if (VEC && c + 1 < n_assets) {
+                const double2 p = *reinterpret_cast<const double2*>(cur);
+                const double2 q = *reinterpret_cast<const double2*>(prv);
+                o.x = log(p.x / q.x);
+                o.y = log(p.y / q.y);
+            } else {
+                o.x = log(cur[0] / prv[0]);
+                if (c + 1 < n_assets) o.y = log(cur[1] / prv[1]);
+            }
         }
-        *reinterpret_cast<double2*>(out + r * ld + c) = o;
+        *reinterpret_cast<double2*>(out + r * ld_out + c) = o;
     }
+    (void)half;
 }
 
-void launch_log_returns(const double* P, double* out, long long rows, int n_assets, int ld, int sm_count,
-                        cudaStream_t st) {
+void launch_log_returns(const double* P, int ld_in, double* out, int ld_out, long long rows, int n_assets,
+                        int sm_count, cudaStream_t st) {
     if (rows <= 0) return;
-    const int threads = 256;
-    long long total = rows * (ld >> 1);
-    long long blocks = (total + threads - 1) / threads;
-    long long cap = (long long)sm_count * 16;
-    if (blocks > cap) blocks = cap;
-    log_returns_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, out, rows, n_assets, ld);
+    const int threads = 128;
+    const int bx = (ld_out / 2 + threads - 1) / threads;
+    long long by = rows;
+    const long long cap = (long long)sm_count * 32 / bx + 1;
+    if (by > cap) by = cap;
+    if (by > 65535) by = 65535;
+    dim3 grid(bx, (unsigned)by);
+    if ((ld_in & 1) == 0)
+        log_returns_kernel<true><<<grid, threads, 0, st>>>(P, ld_in, out, ld_out, rows, n_assets);
+    else
+        log_returns_kernel<false><<<grid, threads, 0, st>>>(P, ld_in, out, ld_out, rows, n_assets);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -192,12 +206,12 @@ __global__ void __launch_bounds__(PREP_THREADS) window_prep_kernel(PrepParams p)
     // ---- prior weights w0 (:679-701 value weighted, :661-677 equally weighted)
     double cs = 0.0;
     if (p.prior_kind == BP_PRIOR_VW) {
-        for (int j = tid; j < N; j += PREP_THREADS) cs += p.caps[(long long)day_row * p.ld + j];
+        for (int j = tid; j < N; j += PREP_THREADS) cs += p.caps[(long long)day_row * p.ld_caps + j];
         cs = block_sum(cs, scratch);
     }
     for (int j = tid; j < p.ldv; j += PREP_THREADS) {
         double v = 0.0;
-        if (j < N) v = p.prior_kind == BP_PRIOR_VW ? p.caps[(long long)day_row * p.ld + j] / cs : 1.0 / (double)N;
+        if (j < N) v = p.prior_kind == BP_PRIOR_VW ? p.caps[(long long)day_row * p.ld_caps + j] / cs : 1.0 / (double)N;
         w0_s[j] = v;
         p.w0[(long long)w * p.ldv + j] = v;
     }

@@ -87,6 +87,7 @@ class BayesEngine:
         rc = self._lib.bp_synchronize(self._h)
         if rc:
             _raise(rc)
+        self._inflight = None
 
     def set_workspace_limit(self, nbytes: int):
         rc = self._lib.bp_set_workspace_limit(self._h, C.c_size_t(int(nbytes)))
@@ -121,8 +122,10 @@ class BayesEngine:
         return int(self._lib.bp_launch_count(self._h))
 
     # ------------------------------------------------------------------ market
-    def upload_market(self, prices, rf_row, caps=None, hf_prices=None, mcm=None):
-        """Host arrays -> HBM.  ``prices`` [D][N], ``rf_row`` [D] (risk-free rate forward-filled onto
+    def upload_market(self, prices, rf_row, caps=None, hf_prices=None, mcm=None, async_copy=False):
+        """Host arrays -> HBM.  With ``async_copy=True`` the arrays must be page-locked and are kept
+        alive by the engine until :meth:`synchronize`; the intraday block then overlaps with stages that
+        do not read it (Jeffreys, daily statistics).  ``prices`` [D][N], ``rf_row`` [D] (risk-free rate forward-filled onto
         the daily rows), ``caps`` [D][N], ``hf_prices`` [R][N], ``mcm`` [n_mcm][D] (row 0 VIX, row 1 EPU)."""
         prices = _c64(prices)
         rf_row = _c64(rf_row)
@@ -163,11 +166,12 @@ class BayesEngine:
             keep.append(mcm)
             desc.mcm = mcm.ctypes.data
             desc.n_mcm = mcm.shape[0]
-        rc = self._lib.bp_upload_market(self._h, C.byref(desc))
+        fn = self._lib.bp_upload_market_async if async_copy else self._lib.bp_upload_market
+        rc = fn(self._h, C.byref(desc))
         if rc:
             _raise(rc)
         self.n_assets, self.n_days, self.n_hf_rows = N, D, int(desc.n_hf_rows)
-        del keep
+        self._inflight = keep if async_copy else None
 
     def prepare_market(self):
         """Re-run the on-device log-return stage (used to time the whole device path)."""
