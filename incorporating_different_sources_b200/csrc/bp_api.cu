@@ -147,6 +147,19 @@ int make_map(bp_handle* h, CUtensorMap* map, const double* base, long long rows,
     return BP_OK;
 }
 
+// 2-D tensor map over a solver workspace of `rows` x ldS doubles (32-row x 16-column boxes)
+int make_solve_map(bp_handle* h, CUtensorMap* map, const double* base, long long rows, int ldS) {
+    cuuint64_t dims[2] = {(cuuint64_t)ldS, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ldS * sizeof(double)};
+    cuuint32_t box[2] = {16, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(BP_ERR_CUDA, "cuTensorMapEncodeTiled (solver workspace) failed with CUresult %d", (int)r);
+    return BP_OK;
+}
+
 int ensure_ws(bp_handle* h, size_t bytes) {
     if (bytes <= h->ws_bytes) return BP_OK;
     if (h->ws) cudaFree(h->ws);
@@ -480,9 +493,11 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
             sp.nu = c.nu;
             sp.weights = c.weights;
             sp.status = c.status;
+            CUtensorMap smap;
+            if ((rc = make_solve_map(h, &smap, c.S, (long long)wc * L.rowsS, L.ldS))) return rc;
             {
                 StageTimer tm(h, BP_STAGE_SOLVE);
-                CU_TRY(launch_chol_solve(sp, h->sm_count, h->stream));
+                CU_TRY(launch_chol_solve(sp, smap, h->sm_count, h->stream));
             }
             h->launches++;
             if ((rc = emit_vec(h, c.weights, L, wc, out->weights ? out->weights + ov : nullptr))) return rc;
@@ -879,7 +894,9 @@ int bp_dense_posterior(bp_handle* h, const bp_dense_problem* in, const bp_dense_
         sp.mode = in->jeffreys ? BP_MODE_JEFFREYS : BP_MODE_CONJUGATE;
         sp.inv_gamma = inv_gamma;
         sp.S = dS; sp.rhs = drhs; sp.scal = dscal; sp.w1 = dw1; sp.nu = dnu; sp.weights = dwts; sp.status = dstatus;
-        CU_TRY(launch_chol_solve(sp, h->sm_count, st));
+        CUtensorMap smap;
+        if ((rc = make_solve_map(h, &smap, dS, rowsS, ldS))) return rc;
+        CU_TRY(launch_chol_solve(sp, smap, h->sm_count, st));
         h->launches++;
     }
     CU_TRY(cudaGetLastError());

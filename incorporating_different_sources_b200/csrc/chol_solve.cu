@@ -7,22 +7,28 @@
 // by S = L L', L z = b, L' w = z (within 1.5e-12 of inv()*b on well-posed inputs) and
 // v1 = w1' S1 w1 = z'z.
 //
-// One CTA per window, left-looking blocked factorisation with 32-column panels, in place in the
-// [rows][ldS] device layout produced by the Gram kernel (lower triangle):
-//   U  panel update   C = S[j0:, j0:j0+32] - L[j0:, :j0] L[j0:j0+32, :j0]'     DMMA, fragments read
-//                     straight from global/L2 as 32-byte vectors (k-permuted, see below)
-//   F  diagonal block 32x32 right-looking Cholesky by one warp (row in registers, warp shuffles,
-//                     rsqrt pivots: the dependent FP64 chain per column is 4 operations)
-//   T  panel solve    L[j0+32:, j0:j0+32] = C * inv(L_d)', one thread per row, L_d broadcast
-//                     from shared memory (same FP64 rate as DMMA on B200, no triangular inverse)
-// The right-hand side rides along as one extra row (row Nr = roundup(N,32)) of the matrix, so the
-// forward substitution L z = b is a by-product of the factorisation.  The back substitution then
-// walks the panels in reverse with coalesced row reads and a warp-level triangular solve.
+// One CTA (4 warps) per window, 4 CTAs per SM, left-looking blocked factorisation with 32-column
+// panels, in place in the [rows][ldS] device layout produced by the Gram kernel (lower triangle):
+//   U  panel update   C = S[j0:, j0:j0+32] - L[j0:, :j0] L[j0:j0+32, :j0]'   on the FP64 tensor cores.
+//                     The already factored columns are streamed through shared memory by TMA
+//                     (2-D tensor map over the whole workspace, 32-row x 16-column boxes,
+//                     SWIZZLE_128B, 3-stage mbarrier ring) in slabs of 8*TPW m-tiles; each warp owns TPW
+//                     8-row m-tiles of the slab and all four 8-column n-tiles of the panel.
+//   F  diagonal block 32x32 right-looking Cholesky + triangular inverse by the whole CTA in shared
+//                     memory (one short pivot chain + a 4-element rank-1 update per thread and step;
+//                     a single warp doing this alone is latency bound and took 2/3 of the kernel)
+//   T  panel solve    L[j0+32:, j0:j0+32] = C * inv(L_d)' on the tensor cores
+// The factor is written with generic stores and re-read by TMA in later panels, so every panel ends
+// with fence.proxy.async + a block barrier.  The right-hand side rides along as one extra row
+// (row Nr = roundup(N,32)) of the matrix, so the forward substitution L z = b is a by-product of
+// the factorisation.  The back substitution then walks the panels in reverse with coalesced row
+// reads and a warp-level triangular solve.
 //
-// k-permutation: of every 16-wide k chunk a lane (g, tig) loads columns {2tig, 2tig+1, 8+2tig,
-// 9+2tig} of its row (two 16-byte loads; a warp-wide load covers whole 32-byte sectors); DMMA step
-// q (0..3) contracts the q-th of those four columns over the four tig lanes.  A and B fragments use
-// the same assignment, so the contraction over the chunk is exact.
+// k-permutation: inside a 16-column chunk, DMMA step q contracts columns {2q, 2q+1, 8+2q, 9+2q}
+// over the four tig lanes.  With the 128-byte swizzle (16-byte unit index XOR row&7) the 16 lanes of
+// a half warp then hit 16 distinct 8-byte words of the 128-byte bank line: every LDS.64 fragment
+// load is conflict free.  A and B fragments use the same assignment, so the contraction is exact.
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -33,132 +39,220 @@ namespace bp {
 constexpr int NB = 32;
 constexpr int LDP = 33;    // padded shared-memory row stride of the 32x32 blocks
 
-struct d4 {
-    double v[4];
-};
+#ifndef CH_NWARPS
+#define CH_NWARPS 4
+#endif
+constexpr int CH_WARPS = CH_NWARPS;                 // warps per window (CTA); 16 / CH_WARPS CTAs per SM
+constexpr int CH_THREADS = CH_WARPS * 32;
 
-// ptr addresses column k0 + 2*tig of the lane's row: the lane takes columns {2tig, 2tig+1, 8+2tig, 9+2tig}
-// of the 16-wide chunk, so each of the two 16-byte loads of a warp covers whole 32-byte sectors
-__device__ __forceinline__ d4 load4(const double* ptr, bool pred) {
-    d4 r;
-    if (pred) {
-        const double2 lo = *reinterpret_cast<const double2*>(ptr);
-        const double2 hi = *reinterpret_cast<const double2*>(ptr + 8);
-        r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = hi.x; r.v[3] = hi.y;
-    } else {
-        r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0.0;
-    }
-    return r;
-}
-// 32x32 Cholesky of the block in Ld (stride LDP) by one warp, right-looking, row `lane` in registers.
-// The FP64 pipe is shared with the DMMAs of the co-resident CTA, so what matters is the length of
-// the dependent FP64 chain: per column it is one shuffle, one rsqrt (no sqrt + divide), one multiply
-// and one FMA; the 496 trailing updates are independent.  Writes L (upper part zeroed) back to Ld and
-// the reciprocal diagonal to invd.  Returns the 1-based index of the first non-positive pivot, or 0.
-__device__ int potrf_warp(double* Ld, double* invd, int lane) {
-    double r[NB];
-#pragma unroll
-    for (int k = 0; k < NB; ++k) r[k] = Ld[lane * LDP + k];
+// 32x32 Cholesky + triangular inverse of the diagonal block in Ld (stride LDP) by the WHOLE CTA.
+// A single warp running this is pure latency (measured: 200k cycles per panel, 2/3 of the kernel, at
+// ~13 cycles per dependent instruction); with 256 threads every step is one short pivot chain
+// (load, rsqrt, multiply, store by warp 0) plus a rank-1 update in which each thread owns 4 elements.
+// Leaves L in Ld (upper part zeroed), 1/diag in invd and inv(L) in Li.  Returns (to every thread)
+// the 1-based index of the first non-positive pivot, or 0.
+__device__ __forceinline__ int potrf_trtri_block(double* Ld, double* Li, double* invd, int tid) {
+    constexpr int TPR = CH_THREADS / NB;   // threads per row of the block
+    constexpr int EPT = NB / TPR;          // consecutive elements owned by a thread
+    const int i = tid / TPR;               // row owned by this thread
+    const int jb = (tid % TPR) * EPT;      // its EPT consecutive columns
     int fail = 0;
-#pragma unroll
+    // One barrier per step: every thread reads the UNSCALED column k and the pivot, derives its own
+    // l_i and l_j (the rsqrt is recomputed by all threads instead of being broadcast through another
+    // barrier) and updates its 4 trailing elements (columns > k: nobody reads those in this step).
+    // The scaled column k is written one step later, after the barrier, when nobody reads column k any more.
+    double lprev = 0.0;
     for (int k = 0; k < NB; ++k) {
-        const double piv = __shfl_sync(0xffffffffu, r[k], k);
+        const double piv = Ld[k * LDP + k];
         if (!(piv > 0.0) && fail == 0) fail = k + 1;
         const double inv = rsqrt(piv);
-        const double l = lane > k ? r[k] * inv : (lane == k ? piv * inv : 0.0);
-        r[k] = l;
-        if (lane == k) invd[k] = inv;
+        const double li = i > k ? Ld[i * LDP + k] * inv : (i == k ? piv * inv : 0.0);
+        if (k > 0 && k - 1 >= jb && k - 1 < jb + EPT) Ld[i * LDP + k - 1] = lprev;    // deferred scaled column k-1
+        if (k >= jb && k < jb + EPT) lprev = li;
 #pragma unroll
-        for (int j = k + 1; j < NB; ++j) {
-            const double lj = __shfl_sync(0xffffffffu, l, j);
-            r[j] = fma(-l, lj, r[j]);
+        for (int e = 0; e < EPT; ++e) {
+            const int j = jb + e;
+            if (j > k) Ld[i * LDP + j] = fma(-li, Ld[j * LDP + k] * inv, Ld[i * LDP + j]);
         }
+        if (tid == 0) invd[k] = inv;
+        __syncthreads();
     }
+    if (NB - 1 >= jb && NB - 1 < jb + EPT) Ld[i * LDP + NB - 1] = lprev;
+    __syncthreads();
 #pragma unroll
-    for (int k = 0; k < NB; ++k) Ld[lane * LDP + k] = k <= lane ? r[k] : 0.0;
+    for (int e = 0; e < EPT; ++e)
+        if (jb + e > i) Ld[i * LDP + jb + e] = 0.0;
+    // inverse X = inv(L): column j = tid & 31, the 8 warps split the rows of every update step
+    const int j = tid & 31, part = tid >> 5;
+    for (int r = part; r < NB; r += CH_WARPS) Li[r * LDP + j] = r == j ? 1.0 : 0.0;
+    __syncthreads();
+    double xprev = 0.0;
+    for (int q = 0; q < NB; ++q) {
+        const double xq = Li[q * LDP + j] * invd[q];          // row q is complete (barrier of step q-1)
+        if (part == 0 && q > 0) Li[(q - 1) * LDP + j] = xprev;  // finalise the previous row: nobody reads it now
+        xprev = xq;
+        for (int r = q + 1 + part; r < NB; r += CH_WARPS) Li[r * LDP + j] = fma(-Ld[r * LDP + q], xq, Li[r * LDP + j]);
+        __syncthreads();
+    }
+    if (part == 0) Li[(NB - 1) * LDP + j] = xprev;
+    __syncthreads();
     return fail;
 }
 
-template <int CH_WARPS>
-__global__ void __launch_bounds__(CH_WARPS * 32, 16 / CH_WARPS) chol_solve_kernel(SolveParams p) {
-    constexpr int CH_THREADS = CH_WARPS * 32;
-    extern __shared__ double sm[];
-    double* Ld = sm;                       // [32][33]
-    double* invd = Ld + NB * LDP;          // [32] reciprocal diagonal of the current block (+ padding)
-    double* red = invd + NB * LDP;         // [CH_WARPS][32]
+#ifndef CH_TPW
+#define CH_TPW 4                                     // m-tiles per warp and slab
+#endif
+#ifndef CH_NSTAGES
+#define CH_NSTAGES 2
+#endif
+constexpr int TPW = CH_TPW;
+constexpr int SLAB_TILES = CH_WARPS * TPW;           // m-tiles per slab (one pass of the panel update)
+constexpr int ABOXES = SLAB_TILES / 4;               // 32-row TMA boxes per slab
+constexpr int CH_STAGES = CH_NSTAGES;
+constexpr int BOX_BYTES = 32 * 16 * 8;               // one TMA box: 32 rows x 16 columns of doubles
+constexpr int CH_STAGE_BYTES = (ABOXES + 1) * BOX_BYTES;   // A slab + 1 B box
+constexpr int CH_TMA_SMEM = CH_STAGES * CH_STAGE_BYTES + 1024;
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+// generic-proxy global writes (the factor) must be visible to later async-proxy (TMA) reads
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+__global__ void __launch_bounds__(CH_THREADS, 16 / CH_WARPS)
+chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p) {
+    extern __shared__ unsigned char sm_raw[];
+    __shared__ uint64_t full_bar[CH_STAGES];
+    __shared__ uint64_t empty_bar[CH_STAGES];     // one arrival per consumer warp
+    __shared__ int fail_s;
+    // 1024-byte alignment by pointer arithmetic on the shared array (keeps the shared address space)
+    unsigned char* stage_mem = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
+    double* Ld = reinterpret_cast<double*>(stage_mem + CH_STAGES * CH_STAGE_BYTES);   // [32][33]
+    double* Li = reinterpret_cast<double*>(stage_mem);   // [32][33] inverse of the diagonal block: aliases the TMA
+                                                         // stages, which are idle between the U phases
+    double* invd = Ld + NB * LDP;          // [32] reciprocal diagonal of the current block
+    double* colk = invd + NB;              // [32] scaled pivot column of the current step
+    double* red = colk + NB;               // [CH_WARPS][32]
     double* scratch = red + CH_WARPS * NB; // [40]
     double* xs = scratch + 40;             // [Nr]
-    __shared__ int fail_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tig = lane & 3;
     const int N = p.n_assets;
     const int ld = p.ldS;
     const int Nr = (N + NB - 1) / NB * NB;     // row index of the right-hand side
+    const int rowsS = (int)(p.win_stride / ld);
+
+    if (tid == 0) {
+        tma_prefetch_desc(&smap);
+        for (int s = 0; s < CH_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], CH_WARPS);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+    // per-lane fragment offsets inside a [32][16] swizzled box: row r = 8*t + g, DMMA step q reads column
+    // c = 2q + (tig&1) + 8*(tig>>1): 16-byte unit (q + 4*(tig>>1)) ^ g, 8-byte half tig&1
+    int foff[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) foff[q] = g * 128 + (((q + 4 * (tig >> 1)) ^ g) << 4) + (tig & 1) * 8;
+    uint32_t it = 0;      // chunks consumed so far (mbarrier phase bookkeeping)
+    // optional phase profile (BP_CHOL_PROFILE=1): cycles of thread 0 between phase boundaries
+    long long prof[6] = {0, 0, 0, 0, 0, 0};
+    long long tlast = p.debug ? clock64() : 0;
+#define PROF(k)                                   \
+    if (p.debug && tid == 0) {                    \
+        const long long tn = clock64();           \
+        prof[k] += tn - tlast;                    \
+        tlast = tn;                               \
+    }
 
     for (int w = blockIdx.x; w < p.n_windows; w += gridDim.x) {
         double* S = p.S + (long long)w * p.win_stride;
         const double* rhs = p.rhs + (long long)w * p.ldv;
+        const int grow0 = w * rowsS;           // first row of this window in the tensor map
         if (tid == 0) fail_s = 0;
         for (int j = tid; j < ld; j += CH_THREADS) S[(long long)Nr * ld + j] = j < N ? rhs[j] : 0.0;
+        fence_proxy_async_all();
         __syncthreads();
 
         for (int j0 = 0; j0 < N; j0 += NB) {
             const int mt_total = (Nr + 8 - j0) / 8;        // m-tiles covering rows j0 .. Nr+7
-            // ---------------- U: panel update (4 m-tiles of this warp at a time)
-            for (int qb = warp; qb < mt_total; qb += 4 * CH_WARPS) {
-                double acc[4][4][2];
+            const int nchunks = j0 / 16;
+            // ---------------- U: panel update, one 256-row slab (32 m-tiles) per pass
+            for (int slab0 = 0; slab0 < mt_total; slab0 += SLAB_TILES) {
+                const int slab_tiles = min(SLAB_TILES, mt_total - slab0);
+                const int nboxes = (slab_tiles + 3) >> 2;
+                const int slab_row = j0 + 8 * slab0;
+                double acc[TPW][4][2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < TPW; ++i)
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt) acc[i][nt][0] = acc[i][nt][1] = 0.0;
-                int rowA[4];
-                bool realA[4];
-                int ni = 0;                  // m-tiles this warp really has in this pass (warp-uniform)
+                int ni = 0;                  // m-tiles this warp really has in this slab (warp-uniform)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int q = qb + i * CH_WARPS;
-                    rowA[i] = j0 + 8 * q + g;
-                    realA[i] = q < mt_total && (rowA[i] < N || rowA[i] == Nr);
-                    ni += q < mt_total ? 1 : 0;
-                }
-                for (int k0 = 0; k0 < j0; k0 += 16) {
-                    d4 a[4], b[4];
+                for (int i = 0; i < TPW; ++i) ni += (warp + CH_WARPS * i) < slab_tiles ? 1 : 0;
+
+                auto issue = [&](int c, uint32_t seq) {
+                    const int stage = seq % CH_STAGES;
+                    unsigned char* dst = stage_mem + stage * CH_STAGE_BYTES;
+                    // the stage is free once all consumer warps have released its previous use
+                    if (seq >= CH_STAGES) mbar_wait(&empty_bar[stage], ((seq / CH_STAGES) - 1) & 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nboxes + 1) * BOX_BYTES);
+                    for (int bx = 0; bx < nboxes; ++bx)
+                        tma_load_2d(dst + bx * BOX_BYTES, &smap, 16 * c, grow0 + slab_row + 32 * bx, &full_bar[stage]);
+                    tma_load_2d(dst + ABOXES * BOX_BYTES, &smap, 16 * c, grow0 + j0, &full_bar[stage]);
+                };
+                if (tid == 0)
+                    for (int c = 0; c < CH_STAGES && c < nchunks; ++c) issue(c, it + c);
+
+                for (int c = 0; c < nchunks; ++c, ++it) {
+                    const int stage = it % CH_STAGES;
+                    const unsigned char* sA = stage_mem + stage * CH_STAGE_BYTES;
+                    const unsigned char* sB = sA + ABOXES * BOX_BYTES;
+                    mbar_wait(&full_bar[stage], (it / CH_STAGES) & 1);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        a[i] = load4(S + (long long)rowA[i] * ld + k0 + 2 * tig, realA[i]);
+                    for (int q = 0; q < 4; ++q) {
+                        double b[4];
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) {
-                        const int rb = j0 + 8 * nt + g;
-                        b[nt] = load4(S + (long long)rb * ld + k0 + 2 * tig, rb < N);
-                    }
+                        for (int nt = 0; nt < 4; ++nt)
+                            b[nt] = *reinterpret_cast<const double*>(sB + nt * 1024 + foff[q]);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (i < ni) {        // skip the DMMAs of m-tile slots past the end of the panel
+                        for (int i = 0; i < TPW; ++i) {
+                            if (i < ni) {    // skip the m-tile slots past the end of the slab
+                                const int t = warp + CH_WARPS * i;
+                                const double a = *reinterpret_cast<const double*>(sA + (t >> 2) * BOX_BYTES + (t & 3) * 1024 + foff[q]);
 #pragma unroll
-                            for (int qq = 0; qq < 4; ++qq)
-#pragma unroll
-                                for (int nt = 0; nt < 4; ++nt)
-                                    dmma884(acc[i][nt][0], acc[i][nt][1], a[i].v[qq], b[nt].v[qq]);
+                                for (int nt = 0; nt < 4; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], a, b[nt]);
+                            }
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[stage]);   // this warp is done with the stage
+                    if (tid == 0 && c + CH_STAGES < nchunks) issue(c + CH_STAGES, it + CH_STAGES);
                 }
                 // C = S - acc, masked for padding; diagonal-block tiles go to shared memory
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int q = qb + i * CH_WARPS;
-                    if (q >= mt_total) continue;
-                    const int row = rowA[i];
+                for (int i = 0; i < TPW; ++i) {
+                    const int q = slab0 + warp + CH_WARPS * i;     // m-tile index within the panel
+                    if (i >= ni) continue;
+                    const int row = j0 + 8 * q + g;
+                    const bool real = row < N || row == Nr;
                     const bool in_diag = q < NB / 8;
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt) {
                         const int col = j0 + 8 * nt + 2 * tig;
                         double c0, c1;
-                        if (realA[i]) {
-                            double2 s = make_double2(0.0, 0.0);
-                            if (col < N) s = *reinterpret_cast<const double2*>(S + (long long)row * ld + col);
-                            c0 = col < N ? s.x - acc[i][nt][0] : 0.0;
-                            c1 = col + 1 < N ? s.y - acc[i][nt][1] : 0.0;
+                        if (real) {
+                            double2 sv = make_double2(0.0, 0.0);
+                            if (col < N) sv = *reinterpret_cast<const double2*>(S + (long long)row * ld + col);
+                            c0 = col < N ? sv.x - acc[i][nt][0] : 0.0;
+                            c1 = col + 1 < N ? sv.y - acc[i][nt][1] : 0.0;
                         } else {
                             c0 = row == col ? 1.0 : 0.0;
                             c1 = row == col + 1 ? 1.0 : 0.0;
@@ -167,52 +261,89 @@ __global__ void __launch_bounds__(CH_WARPS * 32, 16 / CH_WARPS) chol_solve_kerne
                             const int lr = 8 * q + g, lc = 8 * nt + 2 * tig;
                             Ld[lr * LDP + lc] = c0;
                             Ld[lr * LDP + lc + 1] = c1;
-                        } else if (realA[i] && col < N) {
+                        } else if (real && col < N) {
                             *reinterpret_cast<double2*>(S + (long long)row * ld + col) = make_double2(c0, c1);
                         }
                     }
                 }
             }
             __syncthreads();
+            PROF(0)
             // ---------------- F: diagonal block
-            if (warp == 0) {
-                const int f = potrf_warp(Ld, invd, lane);
-                if (lane == 0 && f != 0 && fail_s == 0) fail_s = j0 + f;
+            {
+                const int f = potrf_trtri_block(Ld, Li, invd, tid);
+                if (tid == 0 && f != 0 && fail_s == 0) fail_s = j0 + f;
             }
-            __syncthreads();
+            PROF(1)
             // write L_d back (lower part, real rows only)
             for (int i = warp; i < NB; i += CH_WARPS) {
                 const int row = j0 + i, col = j0 + lane;
                 if (row < N && col < N && lane <= i) S[(long long)row * ld + col] = Ld[i * LDP + lane];
             }
             // ---------------- T: rows below the diagonal block (and the right-hand-side row):
-            // x L_d' = c, one thread per row, right-looking so that the 496 updates are independent
+            // X = C * inv(L_d)' on the tensor cores; C tiles are re-read from global as A fragments with
+            // the same k-permutation as the panel update, B[k][n] = inv(L_d)[n][k] comes from shared memory
             {
-                const int nbelow = N - (j0 + NB) > 0 ? N - (j0 + NB) : 0;
-                for (int e = tid; e < nbelow + 1; e += CH_THREADS) {
-                    const int row = e < nbelow ? j0 + NB + e : Nr;
-                    double* prow = S + (long long)row * ld + j0;
-                    double pv[NB];
+                // the C tile of one m-tile as A fragments: local columns cA, cA+1, cA+8, cA+9 of both 16-wide halves
+                auto load_tile = [&](int q, double (&a)[8]) {
+                    const int row = j0 + 8 * q + g;
+                    const bool real = q < mt_total && (row < N || row == Nr);
 #pragma unroll
-                    for (int c = 0; c < NB; c += 2) {
-                        double2 v = make_double2(0.0, 0.0);
-                        if (j0 + c < N) v = *reinterpret_cast<const double2*>(prow + c);
-                        pv[c] = v.x;
-                        pv[c + 1] = v.y;
+                    for (int kc = 0; kc < 2; ++kc) {
+                        const int cA = 16 * kc + 2 * tig;
+                        double2 lo = make_double2(0.0, 0.0), hi = make_double2(0.0, 0.0);
+                        if (real) {
+                            const double* src = S + (long long)row * ld + j0 + cA;
+                            if (j0 + cA < N) lo = *reinterpret_cast<const double2*>(src);
+                            if (j0 + cA + 8 < N) hi = *reinterpret_cast<const double2*>(src + 8);
+                        }
+                        a[4 * kc + 0] = lo.x;
+                        a[4 * kc + 1] = j0 + cA + 1 < N ? lo.y : 0.0;
+                        a[4 * kc + 2] = hi.x;
+                        a[4 * kc + 3] = j0 + cA + 9 < N ? hi.y : 0.0;
+                    }
+                };
+                double a_cur[8], a_nxt[8];
+                int q = NB / 8 + warp;
+                load_tile(q, a_cur);
+                for (; q < mt_total; q += CH_WARPS) {
+                    load_tile(q + CH_WARPS, a_nxt);          // next tile's loads fly during this tile's DMMAs
+                    const int row = j0 + 8 * q + g;
+                    const bool real = row < N || row == Nr;
+                    double acc[4][2];
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+#pragma unroll
+                    for (int kc = 0; kc < 2; ++kc) {
+                        const int cA = 16 * kc + 2 * tig;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int k = cA + (e & 1) + 8 * (e >> 1);
+                            // this step contracts the 8-wide k block kb; inv(L_d)[n][k] = 0 for k > n, so
+                            // n-tiles left of the k block contribute nothing
+                            const int kb = 2 * kc + (e >> 1);
+#pragma unroll
+                            for (int nt = 0; nt < 4; ++nt)
+                                if (nt >= kb)
+                                    dmma884(acc[nt][0], acc[nt][1], a_cur[4 * kc + e], Li[(8 * nt + g) * LDP + k]);
+                        }
+                    }
+                    __syncwarp();    // every lane holds its part of the tile in registers before it is overwritten
+                    if (real) {
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) {
+                            const int col = j0 + 8 * nt + 2 * tig;
+                            if (col < N)
+                                *reinterpret_cast<double2*>(S + (long long)row * ld + col) = make_double2(acc[nt][0], acc[nt][1]);
+                        }
                     }
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) {
-                        const double x = pv[c] * invd[c];
-                        pv[c] = x;
-#pragma unroll
-                        for (int j = c + 1; j < NB; ++j) pv[j] = fma(-x, Ld[j * LDP + c], pv[j]);
-                    }
-#pragma unroll
-                    for (int c = 0; c < NB; c += 2)
-                        if (j0 + c < N) *reinterpret_cast<double2*>(prow + c) = make_double2(pv[c], pv[c + 1]);
+                    for (int e = 0; e < 8; ++e) a_cur[e] = a_nxt[e];
                 }
             }
+            fence_proxy_async_all();        // the factor written above is read by TMA in the next panels
             __syncthreads();
+            PROF(2)
         }
 
         // ---------------- z = L^-1 b sits in row Nr;  v1 = z'z = w1' S1 w1   (:574)
@@ -228,9 +359,18 @@ __global__ void __launch_bounds__(CH_WARPS * 32, 16 / CH_WARPS) chol_solve_kerne
         for (int j0 = Nr - NB; j0 >= 0; j0 -= NB) {
             double part = 0.0;
             const int col = j0 + lane;
-            if (col < N)
-                for (int i = j0 + NB + warp; i < N; i += CH_WARPS)
-                    part = fma(S[(long long)i * ld + col], xs[i], part);
+            if (col < N) {
+                int i = j0 + NB + warp;
+                for (; i + 3 * CH_WARPS < N; i += 4 * CH_WARPS) {        // 4 independent loads in flight
+                    const double s0 = S[(long long)i * ld + col], s1 = S[(long long)(i + CH_WARPS) * ld + col];
+                    const double s2 = S[(long long)(i + 2 * CH_WARPS) * ld + col], s3 = S[(long long)(i + 3 * CH_WARPS) * ld + col];
+                    part = fma(s0, xs[i], part);
+                    part = fma(s1, xs[i + CH_WARPS], part);
+                    part = fma(s2, xs[i + 2 * CH_WARPS], part);
+                    part = fma(s3, xs[i + 3 * CH_WARPS], part);
+                }
+                for (; i < N; i += CH_WARPS) part = fma(S[(long long)i * ld + col], xs[i], part);
+            }
             red[warp * NB + lane] = part;
             for (int i = warp; i < NB; i += CH_WARPS) {
                 const int row = j0 + i;
@@ -256,6 +396,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32, 16 / CH_WARPS) chol_solve_kerne
             __syncthreads();
         }
 
+        PROF(3)
         // ---------------- posterior scalars and weights
         double* scal = p.scal + (long long)w * BP_S_COUNT;
         double mult = 1.0;
@@ -275,31 +416,44 @@ __global__ void __launch_bounds__(CH_WARPS * 32, 16 / CH_WARPS) chol_solve_kerne
             p.status[w] = fail_s;
         }
         __syncthreads();
+        PROF(4)
     }
+    if (p.debug && tid == 0)
+        for (int k = 0; k < 6; ++k) atomicAdd(reinterpret_cast<unsigned long long*>(p.debug) + k, (unsigned long long)prof[k]);
+#undef PROF
 }
 
-template <int CH_WARPS>
-static cudaError_t launch_chol_t(const SolveParams& p, int sm_count, cudaStream_t st) {
-    const int Nr = (p.n_assets + NB - 1) / NB * NB;
-    const size_t smem = sizeof(double) * (size_t)(2 * NB * LDP + CH_WARPS * NB + 40 + Nr);
-    cudaError_t e = cudaFuncSetAttribute(chol_solve_kernel<CH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+size_t chol_smem_bytes(int n_assets) {
+    const int Nr = (n_assets + NB - 1) / NB * NB;
+    return (size_t)CH_TMA_SMEM + sizeof(double) * (size_t)(NB * LDP + 2 * NB + CH_WARPS * NB + 40 + Nr);
+}
+
+cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int sm_count, cudaStream_t st) {
+    if (p.n_windows <= 0) return cudaSuccess;
+    const size_t smem = chol_smem_bytes(p.n_assets);
+    cudaError_t e = cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int grid = (16 / CH_WARPS) * sm_count;
     if (grid > p.n_windows) grid = p.n_windows;
-    chol_solve_kernel<CH_WARPS><<<grid, CH_WARPS * 32, smem, st>>>(p);
+    static const bool profile = getenv("BP_CHOL_PROFILE") != nullptr;
+    if (profile) {
+        SolveParams q = p;
+        static long long* dbg = nullptr;
+        if (!dbg) cudaMalloc(&dbg, 6 * sizeof(long long));
+        cudaMemsetAsync(dbg, 0, 6 * sizeof(long long), st);
+        q.debug = dbg;
+        chol_solve_kernel<<<grid, CH_THREADS, smem, st>>>(smap, q);
+        long long hostv[6];
+        cudaMemcpyAsync(hostv, dbg, sizeof(hostv), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        const double tot = (double)(hostv[0] + hostv[1] + hostv[2] + hostv[3] + hostv[4]);
+        fprintf(stderr, "[chol profile] W=%d U=%.1f%% F=%.1f%% T=%.1f%% backsub=%.1f%% out=%.1f%% cycles/window=%.0f\n", p.n_windows,
+                100 * hostv[0] / tot, 100 * hostv[1] / tot, 100 * hostv[2] / tot, 100 * hostv[3] / tot, 100 * hostv[4] / tot,
+                tot / p.n_windows);
+        return cudaGetLastError();
+    }
+    chol_solve_kernel<<<grid, CH_THREADS, smem, st>>>(smap, p);
     return cudaGetLastError();
-}
-
-cudaError_t launch_chol_solve(const SolveParams& p, int sm_count, cudaStream_t st) {
-    if (p.n_windows <= 0) return cudaSuccess;
-    static int warps = [] {
-        const char* e = getenv("BP_CHOL_WARPS");      // tuning knob: warps per window (CTA), 16/warps CTAs per SM
-        const int v = e ? atoi(e) : 4;
-        return (v == 2 || v == 4 || v == 8) ? v : 4;
-    }();
-    if (warps == 2) return launch_chol_t<2>(p, sm_count, st);
-    if (warps == 4) return launch_chol_t<4>(p, sm_count, st);
-    return launch_chol_t<8>(p, sm_count, st);
 }
 
 }  // namespace bp

@@ -104,8 +104,9 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                  const GramParams p) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t full_bar[GRAM_STAGES];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 1024-byte alignment for the 128B swizzle, by pointer arithmetic on the shared array itself so that
+    // the compiler keeps the shared address space (an integer round trip degrades every LDS to a generic LD)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;

@@ -95,6 +95,7 @@ struct SolveParams {
     double* nu;              // [W][ldv]
     double* weights;         // [W][ldv]
     int* status;             // [W] 0 = ok, k+1 = non-positive pivot at column k
+    long long* debug;        // optional phase-cycle counters (BP_CHOL_PROFILE), normally nullptr
 };
 
 struct DenseParams {
@@ -129,6 +130,6 @@ constexpr int GRAM_KT = 32;        // rows per TMA k-tile
 constexpr int GRAM_TILE = 128;     // output tile edge
 cudaError_t launch_gram(const GramParams& p, const CUtensorMap& map0, const CUtensorMap& map1, int sm_count,
                         cudaStream_t st);
-cudaError_t launch_chol_solve(const SolveParams& p, int sm_count, cudaStream_t st);
+cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int sm_count, cudaStream_t st);
 
 }  // namespace bp
