@@ -147,6 +147,25 @@ int bp_jeffreys_batched(bp_handle* h, const bp_window_batch* b, const bp_outputs
  * _posterior_S / calculate_conjugate_c when nothing is injected (:90-114, :247-430). */
 int bp_moments_batched(bp_handle* h, const bp_window_batch* b, int mode, const bp_outputs* out);
 
+/* Backtest loop body (:1054-1104, :1127-1219) for a whole backtest: daily portfolio simple returns with
+ * weight drift between rebalances, turnover and transaction cost at each rebalance, weight metrics and
+ * the distance to the value-weighted comparison portfolio.  The first rebalance date is the backtest
+ * start (:1166-1167).  All pointers may be host or device. */
+typedef struct {
+    int n_rebalances;            /* R                                                                */
+    const int* reb_row;          /* [R] daily rows of the rebalance dates, ascending (:1166-1176)     */
+    int last_row;                /* daily row of ts_end_date (>= reb_row[R-1]); later days only drift  */
+    const double* weights;       /* [R][N] weights chosen at each rebalance, uploaded column order,
+                                    0 for stocks outside that date's universe                        */
+    const unsigned char* member; /* [R][N] 1 = stock is in that date's universe; NULL = all stocks    */
+    double distance_scale;       /* spec["risk_aversion"] or 1 (:1101)                               */
+    double turnover_cost_bps;    /* spec["turnover_cost"] (:1214)                                    */
+    double* returns;             /* [last_row - reb_row[0]]      portfolio_simple_returns_series      */
+    double* turnover;            /* [R-1]                        portfolio_turnover_series           */
+    double* metrics;             /* [R][5] max_long, max_short, avg_long, avg_short, average distance */
+} bp_backtest_desc;
+int bp_backtest_batched(bp_handle* h, const bp_backtest_desc* d);
+
 /* calculate_excess_log_returns_from_prices (:31-62) of ONE window (b->n_windows == 1):
  * X is [(rolling_window-1)][N]. */
 int bp_excess_returns(bp_handle* h, const bp_window_batch* b, double* X);

@@ -23,7 +23,7 @@ EXPORTED = [
     "bp_prepare_market", "bp_stats_batched", "bp_hf_cov_batched", "bp_conjugate_batched",
     "bp_jeffreys_batched", "bp_set_stage_timing", "bp_get_stage_times",
     "bp_excess_returns", "bp_quadratic_form", "bp_dense_posterior", "bp_moments_batched",
-    "bp_upload_market_async",
+    "bp_upload_market_async", "bp_backtest_batched",
 ]
 BP_NSTAGE = 8
 STAGES = ("logret", "prep", "gram", "solve")
@@ -66,6 +66,15 @@ class DenseResult(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("scalars", "S1", "w1", "nu", "weights", "status")]
 
 
+class BacktestDesc(C.Structure):
+    _fields_ = [
+        ("n_rebalances", C.c_int), ("reb_row", C.c_void_p), ("last_row", C.c_int), ("weights", C.c_void_p),
+        ("member", C.c_void_p),
+        ("distance_scale", C.c_double), ("turnover_cost_bps", C.c_double),
+        ("returns", C.c_void_p), ("turnover", C.c_void_p), ("metrics", C.c_void_p),
+    ]
+
+
 class LibraryMissing(RuntimeError):
     pass
 
@@ -103,6 +112,7 @@ def load():
     lib.bp_set_stage_timing.argtypes = [C.c_void_p, C.c_int]
     lib.bp_get_stage_times.argtypes = [C.c_void_p, c_double_p, C.POINTER(C.c_longlong)]
     lib.bp_moments_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.c_int, C.POINTER(Outputs)]
+    lib.bp_backtest_batched.argtypes = [C.c_void_p, C.POINTER(BacktestDesc)]
     lib.bp_excess_returns.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.c_void_p]
     lib.bp_quadratic_form.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bp_dense_posterior.argtypes = [C.c_void_p, C.POINTER(DenseProblem), C.POINTER(DenseResult)]

@@ -1,0 +1,241 @@
+"""Loop level of the reference (``portfolio_calculations.py:611-658, :941-1238``) on the batched engine.
+
+``backtest_portfolio`` keeps the reference's signature and its three output containers
+(``portfolio_simple_returns_series``, ``portfolio_turnover_series``, ``portfolio_weights_metrics_df``,
+consumed by ``main.py:74-91`` / ``portfolio_evaluation.py``) but evaluates ALL rebalance windows of the
+backtest in one launch sequence and the whole loop body (returns, drift, turnover, cost, metrics) in one
+more kernel, instead of one Python iteration per trading day (:1232-1234).
+
+Host side = calendar / label bookkeeping only: which days rebalance (:1166-1176), which stocks form the
+universe of a date and in which order (:611-658, the cap-descending ``nlargest`` order of F7).
+"""
+from __future__ import annotations
+
+from datetime import timedelta
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+import pandas as pd
+
+from .windows import HF_LOOKBACK_DAYS, ffill_rows, plan_daily_windows
+
+# ``data_handling.extract_unique_tickers(d, d)`` of the reference reads the S&P-500 constituents of a date
+# from a CSV (:619); offline there is no such file, so the universe provider is pluggable.  Default: every
+# column of the market-cap frame.
+UNIVERSE_PROVIDER: Optional[Callable[[pd.Timestamp], List[str]]] = None
+
+
+def _tickers_for(date, stock_market_caps_df):
+    if UNIVERSE_PROVIDER is not None:
+        return list(UNIVERSE_PROVIDER(date))
+    return list(stock_market_caps_df.columns)
+
+
+def get_window_trading_days(portfolio_spec):
+    mult = {"daily": 1, "weekly": 5, "monthly": 22}[portfolio_spec["rolling_window_frequency"]]
+    return portfolio_spec["rolling_window"] * mult
+
+
+def get_k_largest_stocks_market_caps(stock_market_caps_df, stock_prices_df, stock_intraday_prices_df, trading_date_ts,
+                                     portfolio_size, rolling_window_days, rolling_window_frequency):
+    """:611-658 — eligibility filter + ``nlargest(portfolio_size)`` of the caps at the trade date."""
+    tickers_list = _tickers_for(trading_date_ts, stock_market_caps_df)
+    if rolling_window_frequency not in HF_LOOKBACK_DAYS:
+        raise RuntimeError("Unknown rolling window frequency.")                                   # :637
+    days = HF_LOOKBACK_DAYS[rolling_window_frequency]
+    tick = set(tickers_list)
+    caps_cols = set(stock_market_caps_df.columns)
+    intr_cols = set(stock_intraday_prices_df.columns)
+    cand = [s for s in stock_prices_df.columns if s in tick and s in caps_cols and s in intr_cols]
+    win = stock_prices_df.loc[:trading_date_ts, cand].tail(rolling_window_days)
+    ok_prices = win.notna().all(axis=0)
+    intr = stock_intraday_prices_df.loc[(trading_date_ts - timedelta(days=days)):(trading_date_ts + timedelta(days=1)), cand]
+    ok_intr = intr.notna().any(axis=0)
+    eligible = [s for s in cand if ok_prices[s] and ok_intr[s]]
+    if trading_date_ts in stock_market_caps_df.index:
+        daily = stock_market_caps_df.loc[trading_date_ts, eligible].dropna()
+        return daily.nlargest(portfolio_size)
+    raise ValueError(f"The trading date {trading_date_ts} does not exist in the market capitalizations data.")
+
+
+def rebalance_flags(dates: pd.DatetimeIndex, frequency: str) -> np.ndarray:
+    """Which trading days rebalance (:1166-1176): first day always; daily; Wednesday or > 7 days since the
+    last rebalance; month change relative to the last rebalance."""
+    flags = np.zeros(len(dates), dtype=bool)
+    last = None
+    for i, d in enumerate(dates):
+        if last is None or frequency == "daily":
+            reb = True
+        elif frequency == "weekly":
+            reb = d.weekday() == 2 or (d - last).days > 7
+        elif frequency == "monthly":
+            reb = d.month != last.month
+        else:
+            raise ValueError("Unknown rebalancing frequency.")                                    # :1176
+        if reb:
+            flags[i] = True
+            last = d
+    return flags
+
+
+def compute_portfolio_turnover(portfolio_weights_before_df, portfolio_weights_after_df):
+    """:1054-1075 — kept for API compatibility (label bookkeeping; the batched loop computes it on the device)."""
+    m = portfolio_weights_before_df.merge(portfolio_weights_after_df, how="outer", left_index=True, right_index=True,
+                                          suffixes=("_before", "_after")).fillna(0)
+    diff = (m["Weight_before"] - m["Weight_after"]).abs().sum()
+    rf_turn = abs(portfolio_weights_before_df["Weight"].sum() - portfolio_weights_after_df["Weight"].sum())
+    return (diff + rf_turn) / 2
+
+
+def _slice_for_date(trading_date_ts, portfolio_spec, market_data):
+    """The dispatcher's slicing (:954-988)."""
+    caps_all = market_data["stock_market_caps_df"]
+    prices_all = market_data["stock_prices_df"]
+    intr_all = market_data["stock_intraday_prices_df"]
+    k = get_k_largest_stocks_market_caps(caps_all, prices_all, intr_all, trading_date_ts, portfolio_spec["size"],
+                                         get_window_trading_days(portfolio_spec),
+                                         portfolio_spec["rebalancing_frequency"])      # sic (:960)
+    names = k.index
+    caps = caps_all[names.intersection(caps_all.columns)].loc[:trading_date_ts]
+    prices = prices_all[names.intersection(prices_all.columns)].loc[:trading_date_ts]
+    incl = pd.Timestamp(trading_date_ts).replace(hour=23, minute=59, second=59)
+    intr = intr_all[names.intersection(intr_all.columns)]
+    intr = intr.loc[intr.index <= incl]
+    if prices.tail(get_window_trading_days(portfolio_spec)).isna().any().any():
+        raise ValueError("The filtered stock prices contain NA values.")                         # :988
+    return names, caps, prices, intr
+
+
+def calculate_portfolio_weights(trading_date_ts, portfolio_spec, market_data):
+    """:941-1052 — per-date dispatcher for the in-scope strategies (one window per call)."""
+    from . import portfolio_calculations as pc
+    names, caps, prices, intr = _slice_for_date(trading_date_ts, portfolio_spec, market_data)
+    rf = market_data["risk_free_rate_df"]
+    strat = portfolio_spec["weighting_strategy"]
+    if strat == "vw":
+        return pc.calculate_value_weighted_portfolio(portfolio_spec, trading_date_ts, caps)
+    if strat == "ew":
+        return pc.calculate_equally_weighted_portfolio(portfolio_spec, prices)
+    if strat in ("conjugate_hf_vix_vw", "conjugate_hf_vix_ew"):
+        vix = market_data["vix_prices_df"]
+        return pc.calculate_conjugate_hf_mcm_portfolio(portfolio_spec, trading_date_ts, caps, prices, intr,
+                                                       vix.loc[vix.index <= trading_date_ts], rf)
+    if strat in ("conjugate_hf_epu_vw", "conjugate_hf_epu_ew"):
+        epu = market_data["epu_prices_df"]
+        return pc.calculate_conjugate_hf_mcm_portfolio(portfolio_spec, trading_date_ts, caps, prices, intr,
+                                                       epu.loc[epu.index <= trading_date_ts], rf)
+    if strat == "jeffreys":
+        return pc.calculate_jeffreys_portfolio(portfolio_spec, trading_date_ts, prices, rf)
+    if strat in ("shrinkage", "black_litterman", "jorion", "greyserman"):
+        raise NotImplementedError(f"strategy {strat!r} is out of scope of the CUDA path (SURVEY §2)")
+    raise ValueError("Unknown weights spec.")                                                     # :1050
+
+
+def _batched_weights(engine, portfolio_spec, market_data, dates_all, reb_pos, universes):
+    """Weights [R][N_all] (0 outside each date's universe) for every rebalance date, one upload + one batched
+    call per distinct asset set."""
+    prices_df = market_data["stock_prices_df"]
+    caps_df = market_data["stock_market_caps_df"]
+    intr_df = market_data["stock_intraday_prices_df"]
+    rf_df = market_data["risk_free_rate_df"]
+    strat = portfolio_spec["weighting_strategy"]
+    all_cols = list(prices_df.columns)
+    col_pos = {c: i for i, c in enumerate(all_cols)}
+    N_all = len(all_cols)
+    R = len(reb_pos)
+    W = np.zeros((R, N_all))
+    member = np.zeros((R, N_all), dtype=np.uint8)
+    groups: Dict[tuple, List[int]] = {}
+    for r, names in enumerate(universes):
+        idx = tuple(sorted(col_pos[n] for n in names))
+        member[r, list(idx)] = 1
+        groups.setdefault(idx, []).append(r)
+    dates_ns = dates_all.values.astype("datetime64[ns]")
+    rf_row = ffill_rows(dates_ns, rf_df.index.values.astype("datetime64[ns]"), rf_df.iloc[:, 0].to_numpy(dtype=np.float64))
+    hf_ts = intr_df.index.values.astype("datetime64[ns]")
+    conj = strat.startswith("conjugate")
+    if portfolio_spec["rolling_window_frequency"] != "daily" and strat not in ("vw", "ew"):
+        # weekly / monthly windows: per-window facade calls (still the CUDA path, just not batched)
+        for r, pos in enumerate(reb_pos):
+            wdf = calculate_portfolio_weights(dates_all[pos], portfolio_spec, market_data)
+            W[r, [col_pos[n] for n in wdf.index]] = wdf["Weight"].to_numpy()
+        return W, member
+    mcm = np.stack([market_data["vix_prices_df"].reindex(dates_all).iloc[:, 0].to_numpy(dtype=np.float64),
+                    market_data["epu_prices_df"].reindex(dates_all).iloc[:, 0].to_numpy(dtype=np.float64)])
+    for idx, rows in groups.items():
+        cols = list(idx)
+        engine.upload_market(prices=prices_df.to_numpy(dtype=np.float64)[:, cols], rf_row=rf_row,
+                             caps=caps_df.reindex(dates_all).to_numpy(dtype=np.float64)[:, cols],
+                             hf_prices=intr_df.to_numpy(dtype=np.float64)[:, cols] if conj or strat in ("vw", "ew") else None,
+                             mcm=mcm)
+        d_idx = [reb_pos[r] for r in rows]
+        if strat in ("vw", "ew"):
+            spec = dict(portfolio_spec, weighting_strategy="conjugate_hf_vix_" + strat, mcm_scaling=1,
+                        rolling_window=3, rolling_window_frequency="daily", risk_aversion=1)
+            batch = plan_daily_windows(spec, dates_ns, d_idx, hf_ts)
+            w = engine.moments(batch, outputs=("w0",))["w0"]
+        elif conj:
+            batch = plan_daily_windows(portfolio_spec, dates_ns, d_idx, hf_ts)
+            res = engine.conjugate(batch, outputs=("weights", "status"))
+            _raise_on_status(res["status"], dates_all, d_idx)
+            w = res["weights"]
+        elif strat == "jeffreys":
+            batch = plan_daily_windows(portfolio_spec, dates_ns, d_idx, need_hf=False)
+            res = engine.jeffreys(batch, outputs=("weights", "status"))
+            _raise_on_status(res["status"], dates_all, d_idx)
+            w = res["weights"]
+        else:
+            raise ValueError("Unknown weights spec.")
+        for k, r in enumerate(rows):
+            W[r, cols] = w[k]
+    return W, member
+
+
+def _raise_on_status(status, dates_all, d_idx):
+    bad = np.nonzero(status)[0]
+    if len(bad):
+        raise np.linalg.LinAlgError(
+            f"posterior matrix not positive definite at {dates_all[d_idx[bad[0]]].date()} "
+            f"({len(bad)} of {len(d_idx)} windows): the reference's np.linalg.inv would return garbage (SURVEY F6)")
+
+
+def backtest_portfolio(portfolio_spec, ts_start_date, ts_end_date, market_data, engine=None):
+    """:1221-1238 — same signature (plus an optional engine) and the same three output containers."""
+    from . import portfolio_calculations as pc
+    eng = engine or pc._engine()
+    prices_df = market_data["stock_prices_df"]
+    dates_all = prices_df.index
+    in_range = np.nonzero((dates_all >= ts_start_date) & (dates_all <= ts_end_date))[0]
+    if len(in_range) == 0:
+        raise IndexError("no trading dates in the requested range")
+    bt_dates = dates_all[in_range]
+    flags = rebalance_flags(bt_dates, portfolio_spec["rebalancing_frequency"])
+    reb_pos = in_range[flags]
+    universes = []
+    for pos in reb_pos:
+        d = dates_all[pos]
+        k = get_k_largest_stocks_market_caps(market_data["stock_market_caps_df"], prices_df,
+                                             market_data["stock_intraday_prices_df"], d, portfolio_spec["size"],
+                                             get_window_trading_days(portfolio_spec),
+                                             portfolio_spec["rebalancing_frequency"])
+        universes.append(list(k.index))
+    W, member = _batched_weights(eng, portfolio_spec, market_data, dates_all, list(reb_pos), universes)
+    # loop body on the full column set
+    dates_ns = dates_all.values.astype("datetime64[ns]")
+    rf_df = market_data["risk_free_rate_df"]
+    rf_row = ffill_rows(dates_ns, rf_df.index.values.astype("datetime64[ns]"), rf_df.iloc[:, 0].to_numpy(dtype=np.float64))
+    eng.upload_market(prices=prices_df.to_numpy(dtype=np.float64), rf_row=rf_row,
+                      caps=market_data["stock_market_caps_df"].reindex(dates_all).to_numpy(dtype=np.float64))
+    scale = portfolio_spec["risk_aversion"] if portfolio_spec.get("risk_aversion") is not None else 1
+    rets, turnover, metrics = eng.backtest_loop(reb_pos.astype(np.int32), W, distance_scale=scale,
+                                                turnover_cost_bps=portfolio_spec["turnover_cost"],
+                                                member=member, last_row=int(in_range[-1]))
+    name = portfolio_spec["display_name"]
+    reb_dates = dates_all[reb_pos]
+    returns_series = pd.Series(rets, index=bt_dates[1:], dtype="float64", name=name)
+    turnover_series = pd.Series(turnover, index=reb_dates[1:], dtype="float64", name=name)
+    metrics_df = pd.DataFrame(metrics, index=reb_dates, columns=["max_long", "max_short", "avg_long", "avg_short",
+                                                                 "average_distance_to_comparison_portfolio"])
+    return {"portfolio_simple_returns_series": returns_series,
+            "portfolio_turnover_series": turnover_series,
+            "portfolio_weights_metrics_df": metrics_df}

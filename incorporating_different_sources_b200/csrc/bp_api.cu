@@ -777,6 +777,65 @@ int bp_moments_batched(bp_handle* h, const bp_window_batch* b, int mode, const b
     return run_batches(h, b, out, mode, false);
 }
 
+int bp_backtest_batched(bp_handle* h, const bp_backtest_desc* d) {
+    if (!h || !d) return fail(BP_ERR_INVALID, "null argument");
+    if (!h->has_market) return fail(BP_ERR_STATE, "no market uploaded");
+    if (!h->has_caps) return fail(BP_ERR_STATE, "the backtest loop needs market caps (comparison portfolio)");
+    const int R = d->n_rebalances, N = h->N;
+    if (R < 1 || !d->reb_row || !d->weights || !d->returns || !d->turnover || !d->metrics)
+        return fail(BP_ERR_INVALID, "bp_backtest_desc incomplete");
+    if (N > 8 * 256) return fail(BP_ERR_INVALID, "the loop kernel supports at most 2048 assets");
+    if (is_device_ptr(d->reb_row)) return fail(BP_ERR_INVALID, "reb_row must be a host pointer");
+    for (int s = 0; s < R; ++s) {
+        const int r = d->reb_row[s];
+        if (r < 1 || r >= h->D || (s > 0 && r <= d->reb_row[s - 1]))
+            return fail(BP_ERR_INVALID, "reb_row must be ascending rows in [1, n_days)");
+    }
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    if (d->last_row < d->reb_row[R - 1] || d->last_row >= h->D) return fail(BP_ERR_INVALID, "last_row must lie in [reb_row[R-1], n_days)");
+    const int T = d->last_row - d->reb_row[0];
+    // workspace: weights, member, reb_row, returns, turnover, metrics
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t b_w = al(sizeof(double) * (size_t)R * N), b_m = al((size_t)R * N), b_r = al(sizeof(int) * (size_t)R);
+    const size_t b_ret = al(sizeof(double) * (size_t)std::max(T, 1)), b_to = al(sizeof(double) * (size_t)std::max(R - 1, 1));
+    const size_t b_met = al(sizeof(double) * (size_t)R * 5);
+    int rc = ensure_ws(h, b_w + b_m + b_r + b_ret + b_to + b_met + 256);
+    if (rc) return rc;
+    unsigned char* base = h->ws;
+    double* dw = reinterpret_cast<double*>(base);                    base += b_w;
+    unsigned char* dm = base;                                          base += b_m;
+    int* dr = reinterpret_cast<int*>(base);                           base += b_r;
+    double* dret = reinterpret_cast<double*>(base);                   base += b_ret;
+    double* dto = reinterpret_cast<double*>(base);                    base += b_to;
+    double* dmet = reinterpret_cast<double*>(base);
+    const double* wsrc = d->weights;
+    if (!is_device_ptr(d->weights)) {
+        CU_TRY(cudaMemcpyAsync(dw, d->weights, sizeof(double) * (size_t)R * N, cudaMemcpyHostToDevice, st));
+        wsrc = dw;
+    }
+    const unsigned char* msrc = d->member;
+    if (d->member && !is_device_ptr(d->member)) {
+        CU_TRY(cudaMemcpyAsync(dm, d->member, (size_t)R * N, cudaMemcpyHostToDevice, st));
+        msrc = dm;
+    }
+    CU_TRY(cudaMemcpyAsync(dr, d->reb_row, sizeof(int) * (size_t)R, cudaMemcpyHostToDevice, st));
+    LoopParams lp{};
+    lp.n_assets = N; lp.n_rebalances = R; lp.ldw = N;
+    lp.weights = wsrc; lp.member = msrc; lp.reb_row = dr; lp.last_row = d->last_row;
+    lp.prices = h->prices; lp.ld_prices = N; lp.caps = h->caps; lp.ld_caps = N; lp.rf_row = h->rf_row;
+    lp.distance_scale = d->distance_scale; lp.turnover_cost_bps = d->turnover_cost_bps;
+    lp.returns = dret; lp.turnover = dto; lp.metrics = dmet;
+    CU_TRY(launch_backtest_loop(lp, st));
+    h->launches++;
+    if (T > 0 && (rc = emit_raw(h, dret, sizeof(double) * (size_t)T, d->returns))) return rc;
+    if (R > 1 && (rc = emit_raw(h, dto, sizeof(double) * (size_t)(R - 1), d->turnover))) return rc;
+    if ((rc = emit_raw(h, dmet, sizeof(double) * (size_t)R * 5, d->metrics))) return rc;
+    CU_TRY(cudaStreamSynchronize(st));       // the staging copies of host inputs must be consumed before return
+    h->need_sync = false;
+    return BP_OK;
+}
+
 int bp_excess_returns(bp_handle* h, const bp_window_batch* b, double* X) {
     if (!h || !b || !X) return fail(BP_ERR_INVALID, "null argument");
     if (b->n_windows != 1) return fail(BP_ERR_INVALID, "bp_excess_returns handles one window per call");

@@ -113,6 +113,26 @@ struct DenseParams {
     double* scal;          // [BP_S_COUNT]
 };
 
+struct LoopParams {
+    int n_assets, n_rebalances;
+    int ldw;                     // leading dimension of weights
+    const double* weights;       // [R][ldw] weights chosen at each rebalance (0 for non-members)
+    const unsigned char* member; // [R][N] membership of the rebalance universe, or nullptr (= all)
+    const int* reb_row;          // [R] daily row of each rebalance date (ascending)
+    int last_row;                // daily row of the last backtest date (>= reb_row[R-1])
+    const double* prices;        // dense [D][ld_prices]
+    int ld_prices;
+    const double* caps;          // dense [D][ld_caps]
+    int ld_caps;
+    const double* rf_row;        // [D]
+    double distance_scale;       // risk_aversion (or 1) — the reference scales the weights before comparing (:1101-1102)
+    double turnover_cost_bps;
+    double* returns;             // [last_row - reb_row[0]] one per trading day after the first rebalance
+    double* turnover;            // [R-1]
+    double* metrics;             // [R][5]
+};
+cudaError_t launch_backtest_loop(const LoopParams& p, cudaStream_t st);
+
 void launch_excess_returns(const double* lr, int ld, const double* rf_row, int day_row, int span_days, int n_window,
                            int N, double* X, cudaStream_t st);
 void launch_dense_prep(const DenseParams& p, bool jeffreys, cudaStream_t st);

@@ -295,6 +295,54 @@ class BayesEngine:
         return n0, S0
 
 
+    # ------------------------------------------------------------------ loop body
+    def backtest_loop(self, reb_rows, weights, distance_scale: float, turnover_cost_bps: float, member=None,
+                      last_row: Optional[int] = None):
+        """Loop body of ``Portfolio.update_portfolio`` (:1127-1219) for a whole backtest.
+
+        ``reb_rows`` [R] daily rows of the rebalance dates, ``weights`` [R][N] (NumPy, or a CUDA torch tensor
+        as returned by ``conjugate(..., device_out=True)``).  Returns (returns [T], turnover [R-1], metrics [R][5]).
+        """
+        reb = np.ascontiguousarray(reb_rows, dtype=np.int32)
+        R = int(reb.shape[0])
+        N = self.n_assets
+        keep = [reb]
+        if hasattr(weights, "data_ptr"):
+            if tuple(weights.shape) != (R, N) or not weights.is_contiguous():
+                raise ValueError("weights must be a contiguous [R][N] tensor")
+            wptr = weights.data_ptr()
+        else:
+            w = _c64(weights)
+            if w.shape != (R, N):
+                raise ValueError("weights must be [R][N]")
+            keep.append(w)
+            wptr = w.ctypes.data
+        d = _lib.BacktestDesc()
+        d.n_rebalances = R
+        d.reb_row = reb.ctypes.data
+        last_row = int(reb[-1]) if last_row is None else int(last_row)
+        d.last_row = last_row
+        d.weights = wptr
+        d.member = None
+        if member is not None:
+            m = np.ascontiguousarray(member, dtype=np.uint8)
+            if m.shape != (R, N):
+                raise ValueError("member must be [R][N]")
+            keep.append(m)
+            d.member = m.ctypes.data
+        d.distance_scale = float(distance_scale)
+        d.turnover_cost_bps = float(turnover_cost_bps)
+        T = int(last_row - reb[0]) if R else 0
+        rets = np.empty(max(T, 0))
+        to = np.empty(max(R - 1, 0))
+        met = np.empty((R, 5))
+        d.returns, d.turnover, d.metrics = rets.ctypes.data, to.ctypes.data, met.ctypes.data
+        rc = self._lib.bp_backtest_batched(self._h, C.byref(d))
+        del keep
+        if rc:
+            _raise(rc)
+        return rets, to, met
+
     # ------------------------------------------------------------------ single-window building blocks
     def excess_returns(self, batch: WindowBatch) -> np.ndarray:
         """``calculate_excess_log_returns_from_prices`` (:31-62) of a one-window batch."""

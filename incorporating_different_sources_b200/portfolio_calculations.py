@@ -85,13 +85,6 @@ def adjust_stock_prices_window(portfolio_spec, trading_date_ts, k_stock_prices_d
     return win.iloc[-portfolio_spec["rolling_window"]:]
 
 
-class _Window:
-    """Device-resident minimal market of ONE window plus its batch descriptor."""
-
-    def __init__(self, spec, n_rows_required=True):
-        self.spec = spec
-
-
 def _rf_rows(risk_free_rate_df, dates):
     rf_dates = risk_free_rate_df.index.values.astype("datetime64[ns]")
     rf_vals = risk_free_rate_df.iloc[:, 0].to_numpy(dtype=np.float64)
@@ -552,3 +545,15 @@ def calculate_jeffreys_portfolio(portfolio_spec, trading_date_ts, k_stock_prices
     res = eng.jeffreys(batch, outputs=("weights", "status"))
     _check_status(res["status"][0])
     return _weight_frame(res["weights"][0], cols)
+
+
+# ----------------------------------------------------------------------------------------------
+# loop level (:611-658, :941-1238): see backtest.py
+# ----------------------------------------------------------------------------------------------
+from .backtest import (  # noqa: E402,F401
+    backtest_portfolio,
+    calculate_portfolio_weights,
+    compute_portfolio_turnover,
+    get_k_largest_stocks_market_caps,
+    rebalance_flags,
+)

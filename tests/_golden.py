@@ -13,7 +13,9 @@ _market_cache = {}
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Per-window fixtures (the loop-level ``bt_*`` fixtures are handled by test_gpu_backtest.py)."""
+    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+                  if not n.startswith("bt_"))
 
 
 def sha(a):
