@@ -33,7 +33,7 @@ def test_gpu_matches_reference_golden(engine, name):
     from incorporating_different_sources_b200.windows import plan_daily_windows
     z, meta = load_golden(name)
     if not _daily(meta):
-        pytest.skip("weekly windows are covered by test_gpu_weekly.py")
+        pytest.skip("weekly windows: batched engine is daily-only; covered per window by test_gpu_facade.py")
     mkt = market_for(meta)
     spec = meta["spec"]
     conj = spec["weighting_strategy"].startswith("conjugate")
