@@ -73,6 +73,7 @@ struct bp_handle {
     CUtensorMap map_d, map_hf;
     // window descriptors on the device: day_row, span, row0, hf_row0, hf_m
     int* desc = nullptr;
+    int* desc_host = nullptr;          // page-locked staging of the descriptors (read zero-copy by a kernel)
     int desc_cap = 0;
     double* prior_n = nullptr;
     int prior_n_cap = 0;
@@ -250,7 +251,21 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         if (b->mcm_rows < 0 || b->mcm_rows > n) return fail(BP_ERR_INVALID, "mcm_rows must be in [0, rolling_window]");
         if (b->prior_weights == 0 && !h->has_caps) return fail(BP_ERR_STATE, "value-weighted prior needs market caps");
     }
-    std::vector<int> host((size_t)5 * W, 0);
+    if (W > h->desc_cap) {
+        if (h->desc) {
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            cudaFree(h->desc);
+            cudaFreeHost(h->desc_host);
+        }
+        h->desc = nullptr;
+        h->desc_host = nullptr;
+        h->desc_cap = 0;
+        CU_TRY(cudaMalloc(&h->desc, sizeof(int) * 5 * (size_t)W));
+        CU_TRY(cudaHostAlloc(&h->desc_host, sizeof(int) * 5 * (size_t)W, cudaHostAllocDefault));
+        h->desc_cap = W;
+    }
+    int* host = h->desc_host;
+    memset(host, 0, sizeof(int) * 5 * (size_t)W);
     int max_m = 0;
     for (int w = 0; w < W; ++w) {
         const int dr = b->day_row[w];
@@ -272,18 +287,11 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             max_m = std::max(max_m, m);
         }
     }
-    if (W > h->desc_cap) {
-        if (h->desc) {
-            CU_TRY(cudaStreamSynchronize(h->stream));
-            cudaFree(h->desc);
-        }
-        h->desc = nullptr;
-        h->desc_cap = 0;
-        CU_TRY(cudaMalloc(&h->desc, sizeof(int) * 5 * (size_t)W));
-        h->desc_cap = W;
-    }
-    // the staging vector dies at return: make the copy complete before that
-    CU_TRY(cudaMemcpyAsync(h->desc, host.data(), sizeof(int) * 5 * (size_t)W, cudaMemcpyHostToDevice, h->stream));
+    // zero-copy fetch by a kernel on the compute stream (not the copy engine, see fetch_ints_kernel); the
+    // staging buffer is reused by the next call, so wait until it has been consumed
+    launch_fetch_ints(host, h->desc, 5LL * W, h->stream);
+    h->launches++;
+    CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(h->stream));
     if (need_hf && b->prior_n) {
         if (W > h->prior_n_cap) {
@@ -573,6 +581,7 @@ int bp_destroy(bp_handle* h) {
     cudaEventDestroy(h->ev_main);
     cudaEventDestroy(h->ev_hf);
     cudaFree(h->desc);
+    cudaFreeHost(h->desc_host);
     cudaFree(h->prior_n);
     cudaFree(h->ws);
     cudaFree(h->stage);
@@ -698,6 +707,13 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
     CU_TRY(cudaEventRecord(h->ev_main, st));
     CU_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_main, 0));
     int rc;
+    // small daily arrays first: both streams share one host->device copy engine, which serves copies in
+    // issue order, and the Jeffreys / daily stages must not queue behind the 1.6 GB intraday block
+    CU_TRY(cudaMemcpyAsync(h->prices, m->prices, sizeof(double) * (size_t)D * N, cudaMemcpyHostToDevice, st));
+    if (m->caps) CU_TRY(cudaMemcpyAsync(h->caps, m->caps, sizeof(double) * (size_t)D * N, cudaMemcpyHostToDevice, st));
+    if (m->n_mcm > 0)
+        CU_TRY(cudaMemcpyAsync(h->mcm, m->mcm, sizeof(double) * (size_t)m->n_mcm * D, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(h->rf_row, m->rf_row, sizeof(double) * (size_t)D, cudaMemcpyHostToDevice, st));
     if (R > 0) {
         CU_TRY(cudaMemcpyAsync(h->hf_prices, m->hf_prices, sizeof(double) * (size_t)R * N, cudaMemcpyHostToDevice, h->copy_stream));
         launch_log_returns(h->hf_prices, N, h->lr_hf, ld, R, N, h->sm_count, h->copy_stream);
@@ -705,11 +721,6 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
         CU_TRY(cudaEventRecord(h->ev_hf, h->copy_stream));
         h->hf_pending = true;
     }
-    CU_TRY(cudaMemcpyAsync(h->prices, m->prices, sizeof(double) * (size_t)D * N, cudaMemcpyHostToDevice, st));
-    if (m->caps) CU_TRY(cudaMemcpyAsync(h->caps, m->caps, sizeof(double) * (size_t)D * N, cudaMemcpyHostToDevice, st));
-    if (m->n_mcm > 0)
-        CU_TRY(cudaMemcpyAsync(h->mcm, m->mcm, sizeof(double) * (size_t)m->n_mcm * D, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(h->rf_row, m->rf_row, sizeof(double) * (size_t)D, cudaMemcpyHostToDevice, st));
     launch_log_returns(h->prices, N, h->lr_d, ld, D, N, h->sm_count, st);
     h->launches++;
     CU_TRY(cudaGetLastError());

@@ -133,6 +133,7 @@ struct LoopParams {
 };
 cudaError_t launch_backtest_loop(const LoopParams& p, cudaStream_t st);
 
+void launch_fetch_ints(const int* src_host, int* dst, long long n, cudaStream_t st);
 void launch_excess_returns(const double* lr, int ld, const double* rf_row, int day_row, int span_days, int n_window,
                            int N, double* X, cudaStream_t st);
 void launch_dense_prep(const DenseParams& p, bool jeffreys, cudaStream_t st);

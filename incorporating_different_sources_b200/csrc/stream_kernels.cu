@@ -333,6 +333,22 @@ void launch_unpack_vec(const double* v, int ldv, int N, long long W, double* out
 }
 
 // ------------------------------------------------------------------------------------------------
+// Window descriptors travel host -> device through a page-locked host buffer read by this kernel (zero-copy
+// over PCIe) instead of a cudaMemcpy: the host->device copy engine may be busy for tens of milliseconds with
+// the intraday block, and a queued 80 KB descriptor copy would stall every stage that does not even read it.
+__global__ void fetch_ints_kernel(const int* __restrict__ src_host, int* __restrict__ dst, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src_host[i];
+}
+
+void launch_fetch_ints(const int* src_host, int* dst, long long n, cudaStream_t st) {
+    if (n <= 0) return;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 256) blocks = 256;
+    fetch_ints_kernel<<<(unsigned)blocks, 256, 0, st>>>(src_host, dst, n);
+}
+
+// ------------------------------------------------------------------------------------------------
 // calculate_excess_log_returns_from_prices (:31-62) for ONE window: X[k][j] = L[r0+k][j] - a_k
 __global__ void excess_returns_kernel(const double* __restrict__ lr, int ld, const double* __restrict__ rf_row,
                                       int day_row, int span_days, int n_window, int N, double* __restrict__ X) {
