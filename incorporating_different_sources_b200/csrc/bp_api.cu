@@ -74,7 +74,11 @@ struct bp_handle {
     // window descriptors on the device: day_row, span, row0, hf_row0, hf_m
     int* desc = nullptr;
     int* desc_host = nullptr;          // page-locked staging of the descriptors (read zero-copy by a kernel)
-    int desc_cap = 0;
+    size_t desc_cap = 0;               // capacity in ints
+    // block tile stores of the Gram kernel (window-overlap reuse) and the smallest batch that uses them
+    double* store[2] = {nullptr, nullptr};
+    size_t store_cap[2] = {0, 0};      // capacity in doubles
+    int reuse_min_windows = 32;
     double* prior_n = nullptr;
     int prior_n_cap = 0;
     // workspace
@@ -234,7 +238,34 @@ struct Batch {
     const int *day_row = nullptr, *span = nullptr, *row0 = nullptr, *hf_row0 = nullptr, *hf_m = nullptr;
     const double* prior_n = nullptr;
     int mcm_rows = 0;
+    const int* gdesc = nullptr;        // [W][GRAM_DESC_INTS] Gram job descriptors
+    const int* bdesc[2] = {nullptr, nullptr};   // descriptors of the block precompute launches (phase A / B)
+    int nblocks[2] = {0, 0};
 };
+
+// Block grid of one phase: block b covers return rows [off + b*blk, off + (b+1)*blk); blk == 0: no reuse
+struct PhasePlan {
+    int blk = 0, off = 0, bmin = 0, nb = 0;
+};
+
+inline long long floor_div(long long a, long long b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+// split the row range [row0, row0+rows) of a window on the block grid: d[0..5] = head K segment, tail K
+// segment, first block (relative to bmin) and block count
+void plan_phase(int row0, int rows, const PhasePlan& P, int* d, int* b_lo_out = nullptr, int* b_hi_out = nullptr) {
+    d[0] = row0; d[1] = rows; d[2] = 0; d[3] = 0; d[4] = 0; d[5] = 0;
+    if (P.blk <= 0 || rows <= 0) return;
+    const long long r0 = (long long)row0 - P.off, r1 = r0 + rows;
+    const long long b_lo = floor_div(r0 + P.blk - 1, P.blk), b_hi = floor_div(r1, P.blk);
+    if (b_hi <= b_lo) return;
+    d[1] = (int)(b_lo * P.blk - r0);                 // head rows before the first whole block
+    d[2] = (int)(P.off + b_hi * P.blk);              // tail rows after the last whole block
+    d[3] = (int)(r1 - b_hi * P.blk);
+    d[4] = (int)(b_lo - P.bmin);
+    d[5] = (int)(b_hi - b_lo);
+    if (b_lo_out) *b_lo_out = (int)b_lo;
+    if (b_hi_out) *b_hi_out = (int)b_hi;
+}
 
 int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* out) {
     if (!h || !b) return fail(BP_ERR_INVALID, "null handle or batch");
@@ -251,7 +282,56 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         if (b->mcm_rows < 0 || b->mcm_rows > n) return fail(BP_ERR_INVALID, "mcm_rows must be in [0, rolling_window]");
         if (b->prior_weights == 0 && !h->has_caps) return fail(BP_ERR_STATE, "value-weighted prior needs market caps");
     }
-    if (W > h->desc_cap) {
+    // ---- block grids for the window-overlap reuse of the Gram kernel
+    const int npairs_t = ((h->N + GRAM_TILE - 1) / GRAM_TILE) * ((h->N + GRAM_TILE - 1) / GRAM_TILE + 1) / 2;
+    PhasePlan plan[2];
+    if (W >= h->reuse_min_windows) {
+        const int K = n - 1;
+        plan[1].blk = K >= 512 ? 128 : 64;
+        if (K < 2 * plan[1].blk) plan[1].blk = 0;
+        if (need_hf) {
+            // regular intraday calendar: every window has the same number of rows and consecutive windows
+            // advance by a constant stride that divides it -> one block per stride (a trading day of bars)
+            const int H0 = b->hf_hi[0] - b->hf_lo[0];
+            int stride = W > 1 ? b->hf_lo[1] - b->hf_lo[0] : 0;
+            bool regular = stride > 0 && H0 % stride == 0 && H0 >= 2 * stride;
+            for (int w = 0; regular && w < W; ++w)
+                regular = b->hf_hi[w] - b->hf_lo[w] == H0 && (b->hf_lo[w] - b->hf_lo[0]) % stride == 0;
+            if (regular) {
+                plan[0].blk = stride;
+                plan[0].off = b->hf_lo[0] % stride;
+            } else if (H0 >= 3 * 64) {
+                plan[0].blk = 64;
+            }
+        }
+    }
+    // first pass: block ranges touched by the windows
+    for (int ph = 0; ph < 2; ++ph) {
+        if (plan[ph].blk <= 0) continue;
+        long long bmin = (1LL << 40), bmax = -(1LL << 40);
+        for (int w = 0; w < W; ++w) {
+            int d6[6], lo = 0, hi = 0;
+            const int row0 = ph == 0 ? b->hf_lo[w] + 1 : b->day_row[w] - n + 2;
+            const int rows = ph == 0 ? b->hf_hi[w] - b->hf_lo[w] - 1 : n - 1;
+            plan_phase(row0, rows, plan[ph], d6, &lo, &hi);
+            if (d6[5] > 0) { bmin = std::min<long long>(bmin, lo); bmax = std::max<long long>(bmax, hi); }
+        }
+        if (bmax <= bmin) { plan[ph].blk = 0; continue; }
+        plan[ph].bmin = (int)bmin;
+        plan[ph].nb = (int)(bmax - bmin);
+        const size_t need = (size_t)plan[ph].nb * npairs_t * GRAM_BLOCK_TILE_DOUBLES;
+        if (need * sizeof(double) > h->ws_limit / 2) { plan[ph].blk = 0; plan[ph].nb = 0; continue; }   // too big: no reuse
+        if (need > h->store_cap[ph]) {
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            cudaFree(h->store[ph]);
+            h->store[ph] = nullptr;
+            h->store_cap[ph] = 0;
+            CU_TRY(cudaMalloc(&h->store[ph], need * sizeof(double)));
+            h->store_cap[ph] = need;
+        }
+    }
+    const size_t ints_needed = (size_t)(5 + GRAM_DESC_INTS) * W + (size_t)GRAM_DESC_INTS * (plan[0].nb + plan[1].nb);
+    if (ints_needed > h->desc_cap) {
         if (h->desc) {
             CU_TRY(cudaStreamSynchronize(h->stream));
             cudaFree(h->desc);
@@ -260,12 +340,13 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         h->desc = nullptr;
         h->desc_host = nullptr;
         h->desc_cap = 0;
-        CU_TRY(cudaMalloc(&h->desc, sizeof(int) * 5 * (size_t)W));
-        CU_TRY(cudaHostAlloc(&h->desc_host, sizeof(int) * 5 * (size_t)W, cudaHostAllocDefault));
-        h->desc_cap = W;
+        CU_TRY(cudaMalloc(&h->desc, sizeof(int) * ints_needed));
+        CU_TRY(cudaHostAlloc(&h->desc_host, sizeof(int) * ints_needed, cudaHostAllocDefault));
+        h->desc_cap = ints_needed;
     }
     int* host = h->desc_host;
-    memset(host, 0, sizeof(int) * 5 * (size_t)W);
+    memset(host, 0, sizeof(int) * ints_needed);
+    int* gd = host + (size_t)5 * W;                  // Gram job descriptors
     int max_m = 0;
     for (int w = 0; w < W; ++w) {
         const int dr = b->day_row[w];
@@ -285,11 +366,26 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             host[(size_t)3 * W + w] = lo + 1;        // first HF return row: the window's first bar has no return (F5)
             host[(size_t)4 * W + w] = m;
             max_m = std::max(max_m, m);
+            plan_phase(lo + 1, m, plan[0], gd + (size_t)w * GRAM_DESC_INTS);
         }
+        plan_phase(dr - n + 2, n - 1, plan[1], gd + (size_t)w * GRAM_DESC_INTS + 6);
     }
+    // descriptors of the block precompute launches: one pseudo-window per block, rows of that block only
+    int* bd = gd + (size_t)W * GRAM_DESC_INTS;
+    for (int ph = 0; ph < 2; ++ph) {
+        for (int k = 0; k < plan[ph].nb; ++k) {
+            int* d = bd + (size_t)k * GRAM_DESC_INTS + 6 * ph;
+            d[0] = plan[ph].off + (plan[ph].bmin + k) * plan[ph].blk;
+            d[1] = plan[ph].blk;
+        }
+        out->bdesc[ph] = plan[ph].nb ? h->desc + (bd - host) : nullptr;
+        out->nblocks[ph] = plan[ph].nb;
+        bd += (size_t)plan[ph].nb * GRAM_DESC_INTS;
+    }
+    out->gdesc = h->desc + (size_t)5 * W;
     // zero-copy fetch by a kernel on the compute stream (not the copy engine, see fetch_ints_kernel); the
     // staging buffer is reused by the next call, so wait until it has been consumed
-    launch_fetch_ints(host, h->desc, 5LL * W, h->stream);
+    launch_fetch_ints(host, h->desc, (long long)ints_needed, h->stream);
     h->launches++;
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(h->stream));
@@ -405,26 +501,41 @@ GramParams gram_params(const bp_handle* h, const Batch& B, const Layout& L, cons
     g.mirror = 0;
     g.scal = c.scal;
     g.out = c.S;
+    g.desc = B.gdesc + (size_t)w0 * GRAM_DESC_INTS;
+    g.storeA = h->store[0];
+    g.storeB = h->store[1];
     const bool hf = kind == GRAM_S0 || kind == GRAM_S1;
     const bool daily = kind != GRAM_S0;
+    g.use_phaseA = hf;
+    g.use_phaseB = daily;
     if (hf) {
-        g.seg0_row0 = B.hf_row0 + w0;
-        g.seg0_rows = B.hf_m + w0;
         g.use_alpha = 1;
         g.use_beta = 1;          // beta = alpha*m, g = hbar
         g.gvec = c.gvec;
     }
-    if (daily) {
-        g.seg1_row0 = B.row0 + w0;
-        g.seg1_rows = nullptr;
-        g.seg1_rows_const = B.n - 1;
-        g.pvec = c.pvec;
-    }
+    if (daily) g.pvec = c.pvec;
     if (kind == GRAM_J) {
         g.use_beta = 1;          // beta = 1/n, g = t
         g.gvec = c.gvec;
     }
     return g;
+}
+
+// block precompute: the Gram tile of every whole block of a phase, written fragment-major into the store
+int run_block_precompute(bp_handle* h, const Batch& B, int ph) {
+    if (B.nblocks[ph] <= 0) return BP_OK;
+    GramParams g{};
+    g.n_windows = B.nblocks[ph];
+    g.n_assets = h->N;
+    g.desc = B.bdesc[ph];
+    g.use_phaseA = ph == 0;
+    g.use_phaseB = ph == 1;
+    g.tile_store_out = 1;
+    g.out = h->store[ph];
+    StageTimer tm(h, BP_STAGE_GRAM);
+    CU_TRY(launch_gram(g, h->map_hf, h->map_d, h->sm_count, h->stream));
+    h->launches++;
+    return BP_OK;
 }
 
 int run_gram(bp_handle* h, const GramParams& g) {
@@ -458,6 +569,11 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
     if (solve && mode == BP_MODE_CONJUGATE && !(b->risk_aversion != 0.0))
         return fail(BP_ERR_INVALID, "risk_aversion must be non-zero");
 
+    const bool any_gram = out->T || out->S0 || out->S1 || solve;
+    if (any_gram) {
+        if (mode == BP_MODE_CONJUGATE && (out->S0 || out->S1 || solve) && (rc = run_block_precompute(h, B, 0))) return rc;
+        if ((out->T || out->S1 || solve) && (rc = run_block_precompute(h, B, 1))) return rc;
+    }
     for (int w0 = 0; w0 < B.W; w0 += Wc) {
         const int wc = std::min(Wc, B.W - w0);
         const size_t ov = (size_t)w0 * N, om = (size_t)w0 * N * N;
@@ -582,6 +698,8 @@ int bp_destroy(bp_handle* h) {
     cudaEventDestroy(h->ev_hf);
     cudaFree(h->desc);
     cudaFreeHost(h->desc_host);
+    cudaFree(h->store[0]);
+    cudaFree(h->store[1]);
     cudaFree(h->prior_n);
     cudaFree(h->ws);
     cudaFree(h->stage);

@@ -2,19 +2,28 @@
 //
 // For every rebalance window w and every lower-triangular 128x128 output tile (ti >= tj):
 //
-//   C  = alpha_w * R0[r0:r0+k0, I]' R0[r0:r0+k0, J]      segment 0: intraday log returns (HF prior,
-//                                                         portfolio_calculations.py:314-318)
-//      +           R1[r1:r1+k1, I]' R1[r1:r1+k1, J]      segment 1: daily log returns (:180-182)
-//   out_ij = C_ij - p_i - p_j - beta_w * g_i * g_j        epilogue: rank-2 risk-free correction (:48-57),
-//                                                         HF demeaning (:317) or Jeffreys t t'/n (:600-601)
+//   C  = alpha_w * R0[A rows, I]' R0[A rows, J]           phase A: intraday log returns (HF prior,
+//                                                          portfolio_calculations.py:314-318)
+//      +           R1[B rows, I]' R1[B rows, J]           phase B: daily log returns (:180-182)
+//   out_ij = C_ij - p_i - p_j - beta_w * g_i * g_j         epilogue: rank-2 risk-free correction (:48-57),
+//                                                          HF demeaning (:317) or Jeffreys t t'/n (:600-601)
 //
 // so one launch produces T, S0, S1 = S0 + T (:358) or the Jeffreys matrix directly; S0 and T are
 // never materialised on the fused path.  R0 / R1 are the *shared* log-return matrices of the whole
-// backtest: overlapping windows re-read the same rows through L2, HBM sees each row about once.
+// backtest: a window is a row range.
+//
+// Overlapping windows share almost all of their rows (consecutive rebalance dates differ by one daily
+// row / one day of intraday bars), so the row range of a phase is split on a fixed block grid:
+//   * rows inside whole blocks are NOT contracted again: the block's 128x128 Gram tile was computed once
+//     (same kernel, tile_store_out mode) and is streamed from L2 into the accumulators ("ADD" items,
+//     64 KB halves by cp.async.bulk into the same stage ring);
+//   * only the partial head / tail rows of the window go through the tensor cores ("K" items).
+// All terms are still exact FP64 sums of the same products, only associated differently (no subtraction,
+// no running update), so the result differs from a from-scratch contraction by a few ulp.
 //
 // Data movement: 3-D tensor maps (16-column group, row, group) with SWIZZLE_128B; one
 // cp.async.bulk.tensor per 32-row x 128-column operand tile, 3-stage mbarrier ring that runs ahead
-// across job boundaries (the next job's tiles are in flight during the epilogue).
+// across job boundaries (the next job's items are in flight during the epilogue).
 // Math: 8 warps, 64x32 warp tiles, mma.sync.m8n8k4.f64.  The summation index inside an 8-row group
 // is permuted (lane tig reads row 2*tig+s) which makes every LDS.64 fragment load bank-conflict
 // free under the 128B swizzle; A and B use the same permutation so the product is unchanged.
@@ -27,16 +36,25 @@ constexpr int GRAM_THREADS = 256;
 constexpr int GRAM_STAGES = 3;
 constexpr int CG_BYTES = GRAM_KT * 128;              // one 16-column group: [KT rows][16 doubles]
 constexpr int TILE_BYTES = 8 * CG_BYTES;             // 128 columns
-constexpr int STAGE_BYTES = 2 * TILE_BYTES;          // A tile + B tile
+constexpr int STAGE_BYTES = 2 * TILE_BYTES;          // A tile + B tile (= half of a stored block tile)
 constexpr int GRAM_SMEM = GRAM_STAGES * STAGE_BYTES + 1024;
+static_assert(STAGE_BYTES == GRAM_BLOCK_TILE_DOUBLES * 8 / 2, "an ADD item is half of a stored tile");
 
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// One job = (window, tile pair).  Its items, in order:
+//   group 0/1: K items of phase A segments 0/1     group 2: ADD items of phase A (2 per block)
+//   group 3/4: K items of phase B segments 0/1     group 5: ADD items of phase B
 struct JobState {
-    int job;
-    int w, ti, tj;
-    int row0_0, row0_1;   // first row of segment 0 / 1
-    int rows_0, rows_1;   // row count of segment 0 / 1
-    int nkt0;     // k-tiles of segment 0
-    int nkt;      // k-tiles of both segments
+    int job, w, ti, tj, pair;
+    int row0_0, row0_1, row0_2, row0_3;   // first row of K segment A0, A1, B0, B1
+    int rows_0, rows_1, rows_2, rows_3;   // row counts
+    int blk0_0, blk0_1;                   // first stored block of phase A / B
+    int end0, end1, end2, end3, end4, end5;   // cumulative item counts of the six groups
 };
 
 __device__ __forceinline__ void job_setup(JobState& js, const GramParams& p, int job, int npairs) {
@@ -48,22 +66,35 @@ __device__ __forceinline__ void job_setup(JobState& js, const GramParams& p, int
     js.w = w;
     js.ti = ti;
     js.tj = pr - ti * (ti + 1) / 2;
-    if (p.seg0_row0) {
-        js.row0_0 = p.seg0_row0[w] + p.seg0_row_bias;
-        js.rows_0 = p.seg0_rows[w] + p.seg0_rows_bias;
-    } else {
-        js.row0_0 = 0;
-        js.rows_0 = 0;
-    }
-    if (p.seg1_row0) {
-        js.row0_1 = p.seg1_row0[w] + p.seg1_row_bias;
-        js.rows_1 = p.seg1_rows ? p.seg1_rows[w] : p.seg1_rows_const;
-    } else {
-        js.row0_1 = 0;
-        js.rows_1 = 0;
-    }
-    js.nkt0 = (js.rows_0 + GRAM_KT - 1) / GRAM_KT;
-    js.nkt = js.nkt0 + (js.rows_1 + GRAM_KT - 1) / GRAM_KT;
+    js.pair = pr;
+    const int* d = p.desc + (long long)w * GRAM_DESC_INTS;
+    const bool onA = p.use_phaseA != 0, onB = p.use_phaseB != 0;
+    js.row0_0 = d[0]; js.rows_0 = onA ? d[1] : 0;
+    js.row0_1 = d[2]; js.rows_1 = onA ? d[3] : 0;
+    js.blk0_0 = d[4];
+    const int nblkA = onA ? d[5] : 0;
+    js.row0_2 = d[6]; js.rows_2 = onB ? d[7] : 0;
+    js.row0_3 = d[8]; js.rows_3 = onB ? d[9] : 0;
+    js.blk0_1 = d[10];
+    const int nblkB = onB ? d[11] : 0;
+    int e = 0;
+    e += (js.rows_0 + GRAM_KT - 1) / GRAM_KT; js.end0 = e;
+    e += (js.rows_1 + GRAM_KT - 1) / GRAM_KT; js.end1 = e;
+    e += 2 * nblkA;                           js.end2 = e;
+    e += (js.rows_2 + GRAM_KT - 1) / GRAM_KT; js.end3 = e;
+    e += (js.rows_3 + GRAM_KT - 1) / GRAM_KT; js.end4 = e;
+    e += 2 * nblkB;                           js.end5 = e;
+}
+
+// decode flat item f of a job: group (0..5), index inside the group, and for K items the segment's
+// first row / row count
+__device__ __forceinline__ void item_decode(const JobState& js, int f, int& grp, int& idx, int& row0, int& rows) {
+    if (f < js.end0)      { grp = 0; idx = f;           row0 = js.row0_0; rows = js.rows_0; }
+    else if (f < js.end1) { grp = 1; idx = f - js.end0; row0 = js.row0_1; rows = js.rows_1; }
+    else if (f < js.end2) { grp = 2; idx = f - js.end1; row0 = js.blk0_0; rows = 0; }
+    else if (f < js.end3) { grp = 3; idx = f - js.end2; row0 = js.row0_2; rows = js.rows_2; }
+    else if (f < js.end4) { grp = 4; idx = f - js.end3; row0 = js.row0_3; rows = js.rows_3; }
+    else                  { grp = 5; idx = f - js.end4; row0 = js.blk0_1; rows = 0; }
 }
 
 template <bool MASK>
@@ -99,6 +130,18 @@ __device__ __forceinline__ void compute_tile(const unsigned char* sA, const unsi
     }
 }
 
+// ADD item: half H of a stored tile in fragment-major order (register pair q of thread t at (q*256+t)*16 B):
+// conflict-free LDS.128, every warp takes part
+template <int H>
+__device__ __forceinline__ void add_half(const unsigned char* s, double (&acc)[8][4][2], int tid) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const double2 v = *reinterpret_cast<const double2*>(s + (q * GRAM_THREADS + tid) * 16);
+        acc[H * 4 + (q >> 2)][q & 3][0] += v.x;
+        acc[H * 4 + (q >> 2)][q & 3][1] += v.y;
+    }
+}
+
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_dmma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                  const GramParams p) {
@@ -130,38 +173,49 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const int warp_m0 = (warp & 1) * 64, warp_n0 = (warp >> 1) * 32;
     const int cgA0 = warp_m0 >> 4, cgB0 = warp_n0 >> 4;
 
-    // ---- producer state (thread 0 only): runs GRAM_STAGES tiles ahead of the consumers
+    // ---- producer state (thread 0 only): runs GRAM_STAGES items ahead of the consumers
     JobState pj = {};
-    int pf = 0;          // flat k-tile index inside pj
-    int pit = 0;         // tiles issued so far by this CTA
+    int pf = 0;          // flat item index inside pj
+    int pit = 0;         // items issued so far by this CTA
     bool pvalid = false;
+    auto producer_advance_job = [&](int first) {
+        int nj = first;                      // jobs without items are skipped by producer and consumer alike
+        while (nj < njobs) {
+            job_setup(pj, p, nj, npairs);
+            if (pj.end5 > 0) break;
+            nj += gridDim.x;
+        }
+        pvalid = nj < njobs;
+        pf = 0;
+    };
     auto producer_issue = [&]() {
-        // issue tile (pj, pf) into stage pit % STAGES, then advance
         const int stage = pit % GRAM_STAGES;
         unsigned char* sA = smem + stage * STAGE_BYTES;
-        const int seg = pf < pj.nkt0 ? 0 : 1;
-        const int kt = seg ? pf - pj.nkt0 : pf;
-        const int row = (seg ? pj.row0_1 : pj.row0_0) + kt * GRAM_KT;
-        const void* map = seg ? static_cast<const void*>(&map1) : static_cast<const void*>(&map0);
-        const bool diag = pj.ti == pj.tj;
-        mbar_arrive_expect_tx(&full_bar[stage], diag ? TILE_BYTES : STAGE_BYTES);
-        tma_load_3d(sA, map, 0, row, pj.ti * 8, &full_bar[stage]);
-        if (!diag) tma_load_3d(sA + TILE_BYTES, map, 0, row, pj.tj * 8, &full_bar[stage]);
-        ++pit;
-        if (++pf == pj.nkt) {
-            pf = 0;
-            const int nj = pj.job + gridDim.x;
-            if (nj < njobs) job_setup(pj, p, nj, npairs);
-            else pvalid = false;
+        int grp, idx, row0, rows;
+        item_decode(pj, pf, grp, idx, row0, rows);
+        if (grp == 2 || grp == 5) {
+            const double* store = grp == 2 ? p.storeA : p.storeB;
+            const double* src = store + ((long long)(row0 + (idx >> 1)) * npairs + pj.pair) * GRAM_BLOCK_TILE_DOUBLES +
+                                (idx & 1) * (GRAM_BLOCK_TILE_DOUBLES / 2);
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            bulk_load(sA, src, STAGE_BYTES, &full_bar[stage]);
+        } else {
+            const int row = row0 + idx * GRAM_KT;
+            const void* map = grp < 2 ? static_cast<const void*>(&map0) : static_cast<const void*>(&map1);
+            const bool diag = pj.ti == pj.tj;
+            mbar_arrive_expect_tx(&full_bar[stage], diag ? TILE_BYTES : STAGE_BYTES);
+            tma_load_3d(sA, map, 0, row, pj.ti * 8, &full_bar[stage]);
+            if (!diag) tma_load_3d(sA + TILE_BYTES, map, 0, row, pj.tj * 8, &full_bar[stage]);
         }
+        ++pit;
+        if (++pf == pj.end5) producer_advance_job(pj.job + gridDim.x);
     };
-    if (tid == 0 && (int)blockIdx.x < njobs) {
-        job_setup(pj, p, blockIdx.x, npairs);
-        pvalid = true;
+    if (tid == 0) {
+        producer_advance_job(blockIdx.x);
         for (int s = 0; s < GRAM_STAGES && pvalid; ++s) producer_issue();
     }
 
-    int it = 0;   // tiles consumed so far by this CTA
+    int it = 0;   // items consumed so far by this CTA
     JobState js;
     for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
         job_setup(js, p, job, npairs);
@@ -172,22 +226,28 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
         const bool diag = js.ti == js.tj;
-        for (int f = 0; f < js.nkt; ++f, ++it) {
+        const int nitems = js.end5;
+        for (int f = 0; f < nitems; ++f, ++it) {
             const int stage = it % GRAM_STAGES;
             const uint32_t parity = (it / GRAM_STAGES) & 1;
-            const int seg = f < js.nkt0 ? 0 : 1;
-            const int kt = seg ? f - js.nkt0 : f;
-            const int kvalid = min(GRAM_KT, (seg ? js.rows_1 : js.rows_0) - kt * GRAM_KT);
+            int grp, idx, row0, rows;
+            item_decode(js, f, grp, idx, row0, rows);
             const unsigned char* sA = smem + stage * STAGE_BYTES;
-            const unsigned char* sB = diag ? sA : sA + TILE_BYTES;
             mbar_wait(&full_bar[stage], parity);
-            if (kvalid == GRAM_KT)
-                compute_tile<false>(sA, sB, kvalid, acc, offs0, offs1, cgA0, cgB0, tig);
-            else
-                compute_tile<true>(sA, sB, kvalid, acc, offs0, offs1, cgA0, cgB0, tig);
+            if (grp == 2 || grp == 5) {
+                if (idx & 1) add_half<1>(sA, acc, tid);
+                else add_half<0>(sA, acc, tid);
+            } else {
+                const int kvalid = min(GRAM_KT, rows - idx * GRAM_KT);
+                const unsigned char* sB = diag ? sA : sA + TILE_BYTES;
+                if (kvalid == GRAM_KT)
+                    compute_tile<false>(sA, sB, kvalid, acc, offs0, offs1, cgA0, cgB0, tig);
+                else
+                    compute_tile<true>(sA, sB, kvalid, acc, offs0, offs1, cgA0, cgB0, tig);
+            }
             __syncthreads();                       // every warp is done with this stage
             if (tid == 0 && pvalid) producer_issue();
-            if (seg == 0 && f == js.nkt0 - 1 && p.use_alpha) {
+            if (f == js.end2 - 1 && p.use_alpha) {        // last item of phase A: scale the HF Gram
                 const double alpha = p.scal[(long long)js.w * BP_S_COUNT + BP_S_ALPHA];
 #pragma unroll
                 for (int mt = 0; mt < 8; ++mt)
@@ -197,6 +257,18 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                         acc[mt][nt][1] *= alpha;
                     }
             }
+        }
+
+        if (p.tile_store_out) {
+            // block precompute: raw accumulators, fragment-major, fully coalesced 16-byte stores
+            double* o = p.out + ((long long)js.w * npairs + js.pair) * GRAM_BLOCK_TILE_DOUBLES;
+#pragma unroll
+            for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+                    *reinterpret_cast<double2*>(o + ((mt * 4 + nt) * GRAM_THREADS + tid) * 2) =
+                        make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+            continue;
         }
 
         // ---- epilogue: out_ij = C_ij - p_i - p_j - beta g_i g_j

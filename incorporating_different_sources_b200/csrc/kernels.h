@@ -56,6 +56,14 @@ struct PrepParams {
     long long y_stride;
 };
 
+// Per-window job descriptor of the Gram kernel (GRAM_DESC_INTS ints):
+//   phase A (intraday, scaled by alpha):  [0] A0.row0 [1] A0.rows [2] A1.row0 [3] A1.rows [4] A.block0 [5] A.nblocks
+//   phase B (daily):                      [6] B0.row0 [7] B0.rows [8] B1.row0 [9] B1.rows [10] B.block0 [11] B.nblocks
+// K segments (row0, rows) go through the tensor cores; blocks [block0, block0+nblocks) of the phase's
+// tile store are added from memory.
+constexpr int GRAM_DESC_INTS = 12;
+constexpr int GRAM_BLOCK_TILE_DOUBLES = 128 * 128;   // one stored 128x128 tile, fragment-major
+
 struct GramParams {
     int n_windows;
     int n_assets;        // N
@@ -63,21 +71,18 @@ struct GramParams {
     long long win_stride;    // doubles between consecutive output matrices
     int ldv;
     int mirror;          // also write the upper triangle
-    // segment 0 (HF returns; scaled by alpha afterwards) and segment 1 (daily returns)
-    const int* seg0_row0;    // [W] first row of segment 0 in tensor map 0 (nullptr: no segment 0)
-    const int* seg0_rows;    // [W]
-    const int* seg1_row0;    // [W] (nullptr: no segment 1)
-    const int* seg1_rows;    // [W]
-    int seg0_row_bias;       // added to seg0_row0[w]
-    int seg0_rows_bias;      // added to seg0_rows[w]
-    int seg1_row_bias;
-    int seg1_rows_const;     // if seg1_rows == nullptr: constant row count
-    const double* scal;      // [W][BP_NSCAL] (alpha, beta) ; nullptr -> alpha = 1, beta = 0
+    const int* desc;         // [W][GRAM_DESC_INTS]
+    int use_phaseA;          // contract / add the intraday phase (tensor map 0, storeA)
+    int use_phaseB;          // contract / add the daily phase (tensor map 1, storeB)
+    const double* storeA;    // block tile stores: tile (block b, pair p) at ((b * npairs) + p) * GRAM_BLOCK_TILE_DOUBLES
+    const double* storeB;
+    int tile_store_out;      // 1: block precompute, write raw accumulators fragment-major to out[(w*npairs+pair)*tile]
+    const double* scal;      // [W][BP_S_COUNT] (alpha, beta)
     int use_alpha;
     int use_beta;
     const double* pvec;      // [W][ldv] or nullptr
     const double* gvec;      // [W][ldv] or nullptr
-    double* out;             // [W][win_stride]
+    double* out;             // [W][win_stride]  (or the tile store in tile_store_out mode)
 };
 
 struct SolveParams {
