@@ -122,6 +122,14 @@ long long bp_launch_count(bp_handle* h);
 int bp_set_stage_timing(bp_handle* h, int enable);
 int bp_get_stage_times(bp_handle* h, double* ms /*[BP_NSTAGE]*/, long long* launches /*[BP_NSTAGE]*/);
 
+/* Work counters of the Gram stage since the previous call (then reset): out4[0] window rows contracted on
+ * the tensor cores, [1] precomputed block tiles added, [2] rows contracted by the block precompute, [3] rows
+ * a from-scratch contraction of every window would touch.  bench.py derives executed FLOPs / bytes from them. */
+int bp_get_gram_work(bp_handle* h, double* out4);
+/* Smallest batch (windows) for which the Gram kernel reuses precomputed block tiles between overlapping
+ * windows; INT_MAX disables the reuse (every window is contracted from scratch). Default 32. */
+int bp_set_reuse_min_windows(bp_handle* h, int min_windows);
+
 /* Host -> HBM: replaces the pandas frames of get_market_data() (data_handling.py:270-291).  Also
  * computes both log-return matrices on the device (:37, :314). */
 int bp_upload_market(bp_handle* h, const bp_market_desc* m);

@@ -79,6 +79,8 @@ struct bp_handle {
     double* store[2] = {nullptr, nullptr};
     size_t store_cap[2] = {0, 0};      // capacity in doubles
     int reuse_min_windows = 32;
+    // work counters of the Gram stage since the last bp_get_gram_work (bench.py's roofline accounting)
+    double work_k_rows = 0, work_add_blocks = 0, work_pre_rows = 0, work_full_rows = 0;
     double* prior_n = nullptr;
     int prior_n_cap = 0;
     // workspace
@@ -369,7 +371,13 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             plan_phase(lo + 1, m, plan[0], gd + (size_t)w * GRAM_DESC_INTS);
         }
         plan_phase(dr - n + 2, n - 1, plan[1], gd + (size_t)w * GRAM_DESC_INTS + 6);
+        const int* d = gd + (size_t)w * GRAM_DESC_INTS;
+        auto r8 = [](int r) { return (r + 7) / 8 * 8; };
+        h->work_k_rows += r8(d[1]) + r8(d[3]) + r8(d[7]) + r8(d[9]);
+        h->work_add_blocks += d[5] + d[11];
+        h->work_full_rows += (need_hf ? b->hf_hi[w] - b->hf_lo[w] - 1 : 0) + (n - 1);
     }
+    h->work_pre_rows += (double)plan[0].nb * ((plan[0].blk + 7) / 8 * 8) + (double)plan[1].nb * ((plan[1].blk + 7) / 8 * 8);
     // descriptors of the block precompute launches: one pseudo-window per block, rows of that block only
     int* bd = gd + (size_t)W * GRAM_DESC_INTS;
     for (int ph = 0; ph < 2; ++ph) {
@@ -739,6 +747,22 @@ int bp_device_info(bp_handle* h, int* sm_count, size_t* free_bytes, size_t* tota
 }
 
 long long bp_launch_count(bp_handle* h) { return h ? h->launches : 0; }
+
+int bp_get_gram_work(bp_handle* h, double* out4) {
+    if (!h || !out4) return fail(BP_ERR_INVALID, "null argument");
+    out4[0] = h->work_k_rows;       // window rows contracted on the tensor cores (padded to 8)
+    out4[1] = h->work_add_blocks;   // precomputed block tiles added per tile pair
+    out4[2] = h->work_pre_rows;     // rows contracted by the block precompute launches
+    out4[3] = h->work_full_rows;    // rows a from-scratch contraction of every window would touch
+    h->work_k_rows = h->work_add_blocks = h->work_pre_rows = h->work_full_rows = 0;
+    return BP_OK;
+}
+
+int bp_set_reuse_min_windows(bp_handle* h, int min_windows) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    h->reuse_min_windows = min_windows;
+    return BP_OK;
+}
 
 int bp_set_stage_timing(bp_handle* h, int enable) {
     if (!h) return fail(BP_ERR_INVALID, "null handle");

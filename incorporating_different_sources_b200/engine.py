@@ -117,6 +117,20 @@ class BayesEngine:
             _raise(rc)
         return {name: {"ms": ms[i], "launches": int(cnt[i])} for i, name in enumerate(_lib.STAGES)}
 
+    def gram_work(self) -> Dict[str, float]:
+        """Work counters of the Gram stage since the last call (rows on the tensor cores, block tiles added...)."""
+        out = (C.c_double * 4)()
+        rc = self._lib.bp_get_gram_work(self._h, out)
+        if rc:
+            _raise(rc)
+        return {"k_rows": out[0], "add_blocks": out[1], "precompute_rows": out[2], "full_rows": out[3]}
+
+    def set_reuse_min_windows(self, n: int):
+        """Smallest batch for which overlapping windows share precomputed block Gram tiles (2**31-1 disables)."""
+        rc = self._lib.bp_set_reuse_min_windows(self._h, int(n))
+        if rc:
+            _raise(rc)
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.bp_launch_count(self._h))
