@@ -21,7 +21,7 @@ HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "bayes
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
-]
+] + os.environ.get("BP_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:
