@@ -84,7 +84,26 @@ typedef struct {
     int mcm_rows;               /* MCM observations averaged; 0 = rolling_window (iloc[-n:], :112)   */
     const double* prior_n;      /* [W] injected conjugate_prior_n (the reference's conjugate_prior_n=
                                    argument, :289,:388,:507) or NULL: derive n0 from the MCM series  */
+    int resampled;              /* 1: weekly windows (rolling_window_frequency == "weekly", :151-153): day_row
+                                   and extra_row index the rows defined by bp_set_resampled              */
+    const int* extra_row;       /* [W] resampled windows only: row of the window's LAST return (price at the
+                                   trade date against the previous week's close); the n-2 returns before it
+                                   are the shared weekly rows ending at day_row                         */
+    const int* caps_row;        /* [W] resampled windows only: daily row of the trade date (market caps)  */
 } bp_window_batch;
+
+/* Resampled return rows for weekly windows (adjust_stock_prices_window / calculate_average_mcm_window with
+ * resample('W').last(), :106, :153): row i is ln(P[num_row[i]] / P[den_row[i]]) of the uploaded daily prices
+ * (computed on the device); rf_row / mcm give the risk-free rate (forward-filled at the row's label date,
+ * :54) and the MCM observation of each row.  The host chooses the rows: one per week plus one per trade date. */
+typedef struct {
+    int n_rows;
+    const int* num_row;         /* [n_rows] daily price row in the numerator                             */
+    const int* den_row;         /* [n_rows] daily price row in the denominator (== num_row: zero row)     */
+    const double* rf_row;       /* [n_rows]                                                               */
+    const double* mcm;          /* [n_mcm][n_rows] (n_mcm as uploaded with the market) or NULL            */
+} bp_resampled_desc;
+int bp_set_resampled(bp_handle* h, const bp_resampled_desc* r);
 
 /* Optional outputs (NULL = not wanted).  Vectors are [W][N], matrices [W][N][N] dense symmetric. */
 typedef struct {

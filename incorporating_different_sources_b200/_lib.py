@@ -24,6 +24,7 @@ EXPORTED = [
     "bp_jeffreys_batched", "bp_set_stage_timing", "bp_get_stage_times",
     "bp_excess_returns", "bp_quadratic_form", "bp_dense_posterior", "bp_moments_batched",
     "bp_upload_market_async", "bp_backtest_batched", "bp_get_gram_work", "bp_set_reuse_min_windows",
+    "bp_set_resampled",
 ]
 BP_NSTAGE = 8
 STAGES = ("logret", "prep", "gram", "solve")
@@ -46,7 +47,13 @@ class WindowBatchDesc(C.Structure):
         ("day_row", C.c_void_p), ("span_days", C.c_void_p), ("hf_lo", C.c_void_p), ("hf_hi", C.c_void_p),
         ("mcm_index", C.c_int), ("mcm_scaling", C.c_double), ("risk_aversion", C.c_double),
         ("prior_weights", C.c_int), ("mcm_rows", C.c_int), ("prior_n", C.c_void_p),
+        ("resampled", C.c_int), ("extra_row", C.c_void_p), ("caps_row", C.c_void_p),
     ]
+
+
+class ResampledDesc(C.Structure):
+    _fields_ = [("n_rows", C.c_int), ("num_row", C.c_void_p), ("den_row", C.c_void_p), ("rf_row", C.c_void_p),
+                ("mcm", C.c_void_p)]
 
 
 class Outputs(C.Structure):
@@ -112,6 +119,7 @@ def load():
     lib.bp_set_stage_timing.argtypes = [C.c_void_p, C.c_int]
     lib.bp_get_stage_times.argtypes = [C.c_void_p, c_double_p, C.POINTER(C.c_longlong)]
     lib.bp_moments_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.c_int, C.POINTER(Outputs)]
+    lib.bp_set_resampled.argtypes = [C.c_void_p, C.POINTER(ResampledDesc)]
     lib.bp_get_gram_work.argtypes = [C.c_void_p, c_double_p]
     lib.bp_set_reuse_min_windows.argtypes = [C.c_void_p, C.c_int]
     lib.bp_backtest_batched.argtypes = [C.c_void_p, C.POINTER(BacktestDesc)]

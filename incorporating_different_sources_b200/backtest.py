@@ -17,7 +17,7 @@ from typing import Callable, Dict, List, Optional
 import numpy as np
 import pandas as pd
 
-from .windows import HF_LOOKBACK_DAYS, ffill_rows, plan_daily_windows
+from .windows import HF_LOOKBACK_DAYS, ffill_rows, plan_daily_windows, plan_weekly_windows
 
 # ``data_handling.extract_unique_tickers(d, d)`` of the reference reads the S&P-500 constituents of a date
 # from a CSV (:619); offline there is no such file, so the universe provider is pluggable.  Default: every
@@ -154,12 +154,11 @@ def _batched_weights(engine, portfolio_spec, market_data, dates_all, reb_pos, un
     rf_row = ffill_rows(dates_ns, rf_df.index.values.astype("datetime64[ns]"), rf_df.iloc[:, 0].to_numpy(dtype=np.float64))
     hf_ts = intr_df.index.values.astype("datetime64[ns]")
     conj = strat.startswith("conjugate")
-    if portfolio_spec["rolling_window_frequency"] != "daily" and strat not in ("vw", "ew"):
-        # weekly / monthly windows: per-window facade calls (still the CUDA path, just not batched)
-        for r, pos in enumerate(reb_pos):
-            wdf = calculate_portfolio_weights(dates_all[pos], portfolio_spec, market_data)
-            W[r, [col_pos[n] for n in wdf.index]] = wdf["Weight"].to_numpy()
-        return W, member
+    weekly = portfolio_spec["rolling_window_frequency"] == "weekly" and strat not in ("vw", "ew")
+    if portfolio_spec["rolling_window_frequency"] not in ("daily", "weekly") and strat not in ("vw", "ew"):
+        raise NotImplementedError("monthly windows: resample('M') was removed from pandas (SURVEY F10)")
+    rf_dates = rf_df.index.values.astype("datetime64[ns]")
+    rf_vals = rf_df.iloc[:, 0].to_numpy(dtype=np.float64)
     mcm = np.stack([market_data["vix_prices_df"].reindex(dates_all).iloc[:, 0].to_numpy(dtype=np.float64),
                     market_data["epu_prices_df"].reindex(dates_all).iloc[:, 0].to_numpy(dtype=np.float64)])
     for idx, rows in groups.items():
@@ -175,12 +174,20 @@ def _batched_weights(engine, portfolio_spec, market_data, dates_all, reb_pos, un
             batch = plan_daily_windows(spec, dates_ns, d_idx, hf_ts)
             w = engine.moments(batch, outputs=("w0",))["w0"]
         elif conj:
-            batch = plan_daily_windows(portfolio_spec, dates_ns, d_idx, hf_ts)
+            if weekly:
+                rows_w, batch = plan_weekly_windows(portfolio_spec, dates_ns, d_idx, rf_dates, rf_vals, mcm, hf_ts)
+                engine.set_resampled(rows_w)
+            else:
+                batch = plan_daily_windows(portfolio_spec, dates_ns, d_idx, hf_ts)
             res = engine.conjugate(batch, outputs=("weights", "status"))
             _raise_on_status(res["status"], dates_all, d_idx)
             w = res["weights"]
         elif strat == "jeffreys":
-            batch = plan_daily_windows(portfolio_spec, dates_ns, d_idx, need_hf=False)
+            if weekly:
+                rows_w, batch = plan_weekly_windows(portfolio_spec, dates_ns, d_idx, rf_dates, rf_vals, None, need_hf=False)
+                engine.set_resampled(rows_w)
+            else:
+                batch = plan_daily_windows(portfolio_spec, dates_ns, d_idx, need_hf=False)
             res = engine.jeffreys(batch, outputs=("weights", "status"))
             _raise_on_status(res["status"], dates_all, d_idx)
             w = res["weights"]

@@ -66,6 +66,11 @@ struct bp_handle {
     double *prices = nullptr, *lr_d = nullptr, *caps = nullptr, *hf_prices = nullptr, *lr_hf = nullptr,
            *mcm = nullptr, *rf_row = nullptr;
     bool has_caps = false;
+    // resampled (weekly) return rows: see bp_set_resampled
+    double *lr_w = nullptr, *rf_w = nullptr, *mcm_w = nullptr;
+    int* rs_idx = nullptr;
+    int Rw = 0;
+    CUtensorMap map_w;
     size_t cap_daily = 0, cap_hf = 0, cap_mcm = 0, cap_days = 0;   // allocated sizes (elements) for buffer reuse
     cudaStream_t copy_stream = nullptr;                  // intraday H2D + its log-return kernel
     cudaEvent_t ev_main = nullptr, ev_hf = nullptr;
@@ -124,7 +129,15 @@ struct StageTimer {
 
 namespace {
 
+void free_resampled(bp_handle* h) {
+    cudaFree(h->lr_w); cudaFree(h->rf_w); cudaFree(h->mcm_w); cudaFree(h->rs_idx);
+    h->lr_w = h->rf_w = h->mcm_w = nullptr;
+    h->rs_idx = nullptr;
+    h->Rw = 0;
+}
+
 void free_market(bp_handle* h) {
+    free_resampled(h);
     cudaFree(h->prices); cudaFree(h->lr_d); cudaFree(h->caps); cudaFree(h->hf_prices);
     cudaFree(h->lr_hf); cudaFree(h->mcm); cudaFree(h->rf_row);
     h->prices = h->lr_d = h->caps = h->hf_prices = h->lr_hf = h->mcm = h->rf_row = nullptr;
@@ -240,6 +253,8 @@ struct Batch {
     const int *day_row = nullptr, *span = nullptr, *row0 = nullptr, *hf_row0 = nullptr, *hf_m = nullptr;
     const double* prior_n = nullptr;
     int mcm_rows = 0;
+    bool resampled = false;
+    const int *extra_row = nullptr, *caps_row = nullptr;
     const int* gdesc = nullptr;        // [W][GRAM_DESC_INTS] Gram job descriptors
     const int* bdesc[2] = {nullptr, nullptr};   // descriptors of the block precompute launches (phase A / B)
     int nblocks[2] = {0, 0};
@@ -279,10 +294,16 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
     if (need_hf) {
         if (!b->hf_lo || !b->hf_hi) return fail(BP_ERR_INVALID, "hf_lo / hf_hi missing");
         if (h->R <= 0) return fail(BP_ERR_STATE, "the uploaded market has no intraday prices");
+        if (b->resampled && !b->prior_n && !h->mcm_w) return fail(BP_ERR_STATE, "bp_set_resampled was given no MCM rows");
         if (!b->prior_n && (b->mcm_index < 0 || b->mcm_index >= h->n_mcm))
             return fail(BP_ERR_INVALID, "mcm_index %d out of range", b->mcm_index);
         if (b->mcm_rows < 0 || b->mcm_rows > n) return fail(BP_ERR_INVALID, "mcm_rows must be in [0, rolling_window]");
         if (b->prior_weights == 0 && !h->has_caps) return fail(BP_ERR_STATE, "value-weighted prior needs market caps");
+    }
+    const bool rs = b->resampled != 0;
+    if (rs) {
+        if (h->Rw <= 0) return fail(BP_ERR_STATE, "resampled windows need bp_set_resampled first");
+        if (!b->extra_row || !b->caps_row) return fail(BP_ERR_INVALID, "resampled windows need extra_row and caps_row");
     }
     // ---- block grids for the window-overlap reuse of the Gram kernel
     const int npairs_t = ((h->N + GRAM_TILE - 1) / GRAM_TILE) * ((h->N + GRAM_TILE - 1) / GRAM_TILE + 1) / 2;
@@ -290,7 +311,7 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
     if (W >= h->reuse_min_windows) {
         const int K = n - 1;
         plan[1].blk = K >= 512 ? 128 : 64;
-        if (K < 2 * plan[1].blk) plan[1].blk = 0;
+        if (K < 2 * plan[1].blk || rs) plan[1].blk = 0;      // resampled windows: shared rows + one per-date row, no block reuse
         if (need_hf) {
             // regular intraday calendar: every window has the same number of rows and consecutive windows
             // advance by a constant stride that divides it -> one block per stride (a trading day of bars)
@@ -332,7 +353,7 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             h->store_cap[ph] = need;
         }
     }
-    const size_t ints_needed = (size_t)(5 + GRAM_DESC_INTS) * W + (size_t)GRAM_DESC_INTS * (plan[0].nb + plan[1].nb);
+    const size_t ints_needed = (size_t)(7 + GRAM_DESC_INTS) * W + (size_t)GRAM_DESC_INTS * (plan[0].nb + plan[1].nb);
     if (ints_needed > h->desc_cap) {
         if (h->desc) {
             CU_TRY(cudaStreamSynchronize(h->stream));
@@ -348,18 +369,30 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
     }
     int* host = h->desc_host;
     memset(host, 0, sizeof(int) * ints_needed);
-    int* gd = host + (size_t)5 * W;                  // Gram job descriptors
+    int* gd = host + (size_t)7 * W;                  // Gram job descriptors
     int max_m = 0;
     for (int w = 0; w < W; ++w) {
         const int dr = b->day_row[w];
-        if (dr < n - 1 || dr >= h->D)
-            return fail(BP_ERR_INVALID, "window %d: day_row %d needs %d prior price rows inside [0,%d)", w, dr, n - 1, h->D);
-        if (need_hf && !b->prior_n && dr < (b->mcm_rows ? b->mcm_rows : n) - 1)
+        if (rs) {
+            // shared weekly rows dr-(n-2)+1 .. dr (row 0 is the zero row of the first week) + one per-date row
+            if (dr - (n - 2) + 1 < 1 || dr >= h->Rw)
+                return fail(BP_ERR_INVALID, "window %d: resampled day_row %d needs %d prior rows inside [1,%d)", w, dr, n - 2, h->Rw);
+            if (b->extra_row[w] < 0 || b->extra_row[w] >= h->Rw || b->caps_row[w] < 0 || b->caps_row[w] >= h->D)
+                return fail(BP_ERR_INVALID, "window %d: extra_row / caps_row out of range", w);
+            host[(size_t)5 * W + w] = b->extra_row[w];
+            host[(size_t)6 * W + w] = b->caps_row[w];
+        } else {
+            if (dr < n - 1 || dr >= h->D)
+                return fail(BP_ERR_INVALID, "window %d: day_row %d needs %d prior price rows inside [0,%d)", w, dr, n - 1, h->D);
+            host[(size_t)5 * W + w] = -1;
+            host[(size_t)6 * W + w] = dr;
+        }
+        if (need_hf && !b->prior_n && dr < (b->mcm_rows ? b->mcm_rows : n) - 1 - (rs ? 1 : 0))
             return fail(BP_ERR_INVALID, "window %d: not enough MCM observations before day_row %d", w, dr);
         if (b->span_days[w] <= 0) return fail(BP_ERR_INVALID, "window %d: span_days must be positive", w);
         host[w] = dr;
         host[(size_t)W + w] = b->span_days[w];
-        host[(size_t)2 * W + w] = dr - n + 2;       // first daily RETURN row (F2: n prices -> n-1 returns)
+        host[(size_t)2 * W + w] = rs ? dr - (n - 2) + 1 : dr - n + 2;   // first RETURN row (F2: n prices -> n-1 returns)
         if (need_hf) {
             const int lo = b->hf_lo[w], hi = b->hf_hi[w];
             const int m = hi - lo - 1;
@@ -370,7 +403,13 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             max_m = std::max(max_m, m);
             plan_phase(lo + 1, m, plan[0], gd + (size_t)w * GRAM_DESC_INTS);
         }
-        plan_phase(dr - n + 2, n - 1, plan[1], gd + (size_t)w * GRAM_DESC_INTS + 6);
+        if (rs) {
+            int* d6 = gd + (size_t)w * GRAM_DESC_INTS + 6;
+            d6[0] = dr - (n - 2) + 1; d6[1] = n - 2;       // shared weekly rows
+            d6[2] = b->extra_row[w];  d6[3] = 1;           // the trade date's own row
+        } else {
+            plan_phase(dr - n + 2, n - 1, plan[1], gd + (size_t)w * GRAM_DESC_INTS + 6);
+        }
         const int* d = gd + (size_t)w * GRAM_DESC_INTS;
         auto r8 = [](int r) { return (r + 7) / 8 * 8; };
         h->work_k_rows += r8(d[1]) + r8(d[3]) + r8(d[7]) + r8(d[9]);
@@ -390,7 +429,10 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         out->nblocks[ph] = plan[ph].nb;
         bd += (size_t)plan[ph].nb * GRAM_DESC_INTS;
     }
-    out->gdesc = h->desc + (size_t)5 * W;
+    out->gdesc = h->desc + (size_t)7 * W;
+    out->resampled = rs;
+    out->extra_row = rs ? h->desc + 5 * (size_t)W : nullptr;
+    out->caps_row = h->desc + 6 * (size_t)W;
     // zero-copy fetch by a kernel on the compute stream (not the copy engine, see fetch_ints_kernel); the
     // staging buffer is reused by the next call, so wait until it has been consumed
     launch_fetch_ints(host, h->desc, (long long)ints_needed, h->stream);
@@ -478,15 +520,18 @@ PrepParams prep_params(const bp_handle* h, const bp_window_batch* b, const Batch
     p.ldv = L.ldv;
     p.prior_kind = b->prior_weights == 0 ? BP_PRIOR_VW : BP_PRIOR_EW;
     p.mcm_scaling = b->mcm_scaling;
-    p.lr_daily = h->lr_d;
+    p.lr_daily = B.resampled ? h->lr_w : h->lr_d;
     p.lr_hf = h->lr_hf;
     p.caps = h->has_caps ? h->caps : nullptr;
     p.ld_caps = h->N;
     p.mcm = (mode == BP_MODE_CONJUGATE && h->mcm) ? h->mcm + (size_t)b->mcm_index * h->D : nullptr;
+    if (B.resampled) p.mcm = (mode == BP_MODE_CONJUGATE && h->mcm_w) ? h->mcm_w + (size_t)b->mcm_index * h->Rw : nullptr;
     p.mcm_rows = B.mcm_rows;
     p.prior_n = B.prior_n ? B.prior_n + w0 : nullptr;
-    p.rf_row = h->rf_row;
+    p.rf_row = B.resampled ? h->rf_w : h->rf_row;
     p.day_row = B.day_row + w0;
+    p.extra_row = B.extra_row ? B.extra_row + w0 : nullptr;
+    p.caps_row = B.caps_row ? B.caps_row + w0 : nullptr;
     p.span_days = B.span + w0;
     p.hf_row0 = B.hf_row0 + w0;
     p.hf_m = B.hf_m + w0;
@@ -546,9 +591,9 @@ int run_block_precompute(bp_handle* h, const Batch& B, int ph) {
     return BP_OK;
 }
 
-int run_gram(bp_handle* h, const GramParams& g) {
+int run_gram(bp_handle* h, const GramParams& g, bool resampled) {
     StageTimer tm(h, BP_STAGE_GRAM);
-    CU_TRY(launch_gram(g, h->map_hf, h->map_d, h->sm_count, h->stream));
+    CU_TRY(launch_gram(g, h->map_hf, resampled ? h->map_w : h->map_d, h->sm_count, h->stream));
     h->launches++;
     return BP_OK;
 }
@@ -592,19 +637,19 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
         }
         h->launches++;
         if (out->T) {
-            rc = run_gram(h, gram_params(h, B, L, c, w0, wc, GRAM_T));
+            rc = run_gram(h, gram_params(h, B, L, c, w0, wc, GRAM_T), B.resampled);
             if (rc) return rc;
             rc = emit_sym(h, c.S, L, wc, out->T + om);
             if (rc) return rc;
         }
         if (out->S0 && mode == BP_MODE_CONJUGATE) {
-            rc = run_gram(h, gram_params(h, B, L, c, w0, wc, GRAM_S0));
+            rc = run_gram(h, gram_params(h, B, L, c, w0, wc, GRAM_S0), B.resampled);
             if (rc) return rc;
             rc = emit_sym(h, c.S, L, wc, out->S0 + om);
             if (rc) return rc;
         }
         if (solve || out->S1) {
-            rc = run_gram(h, gram_params(h, B, L, c, w0, wc, mode == BP_MODE_CONJUGATE ? GRAM_S1 : GRAM_J));
+            rc = run_gram(h, gram_params(h, B, L, c, w0, wc, mode == BP_MODE_CONJUGATE ? GRAM_S1 : GRAM_J), B.resampled);
             if (rc) return rc;
             rc = emit_sym(h, c.S, L, wc, out->S1 ? out->S1 + om : nullptr);
             if (rc) return rc;
@@ -842,6 +887,11 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
         h->cap_mcm = need_mcm;
         h->cap_days = (size_t)D;
     }
+    if (h->lr_w) {
+        // resampled rows refer to the previous prices
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        free_resampled(h);
+    }
     h->N = N; h->D = D; h->ld = ld; h->R = R; h->n_mcm = m->n_mcm;
     h->has_caps = m->caps != nullptr;
     cudaStream_t st = h->stream;
@@ -884,6 +934,37 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
 int bp_upload_market(bp_handle* h, const bp_market_desc* m) { return upload_market_impl(h, m, true); }
 
 int bp_upload_market_async(bp_handle* h, const bp_market_desc* m) { return upload_market_impl(h, m, false); }
+
+int bp_set_resampled(bp_handle* h, const bp_resampled_desc* r) {
+    if (!h || !r) return fail(BP_ERR_INVALID, "null argument");
+    if (!h->has_market) return fail(BP_ERR_STATE, "no market uploaded");
+    if (r->n_rows < 2 || !r->num_row || !r->den_row || !r->rf_row) return fail(BP_ERR_INVALID, "bp_resampled_desc incomplete");
+    for (int i = 0; i < r->n_rows; ++i)
+        if (r->num_row[i] < 0 || r->num_row[i] >= h->D || r->den_row[i] < 0 || r->den_row[i] >= h->D)
+            return fail(BP_ERR_INVALID, "resampled row %d references a price row outside [0,%d)", i, h->D);
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    free_resampled(h);
+    const int Rw = r->n_rows;
+    CU_TRY(cudaMalloc(&h->lr_w, sizeof(double) * (size_t)Rw * h->ld));
+    CU_TRY(cudaMalloc(&h->rf_w, sizeof(double) * (size_t)Rw));
+    CU_TRY(cudaMalloc(&h->rs_idx, sizeof(int) * 2 * (size_t)Rw));
+    CU_TRY(cudaMemcpyAsync(h->rs_idx, r->num_row, sizeof(int) * (size_t)Rw, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->rs_idx + Rw, r->den_row, sizeof(int) * (size_t)Rw, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->rf_w, r->rf_row, sizeof(double) * (size_t)Rw, cudaMemcpyHostToDevice, h->stream));
+    if (r->mcm && h->n_mcm > 0) {
+        CU_TRY(cudaMalloc(&h->mcm_w, sizeof(double) * (size_t)h->n_mcm * Rw));
+        CU_TRY(cudaMemcpyAsync(h->mcm_w, r->mcm, sizeof(double) * (size_t)h->n_mcm * Rw, cudaMemcpyHostToDevice, h->stream));
+    }
+    launch_gather_log_returns(h->prices, h->N, h->rs_idx, h->rs_idx + Rw, h->lr_w, h->ld, Rw, h->N, h->stream);
+    h->launches++;
+    CU_TRY(cudaGetLastError());
+    h->Rw = Rw;
+    int rc = make_map(h, &h->map_w, h->lr_w, Rw, h->ld);
+    if (rc) return rc;
+    CU_TRY(cudaStreamSynchronize(h->stream));     // host index arrays may be freed after return
+    return BP_OK;
+}
 
 int bp_conjugate_batched(bp_handle* h, const bp_window_batch* b, const bp_outputs* out) {
     if (!out) return fail(BP_ERR_INVALID, "outputs missing");

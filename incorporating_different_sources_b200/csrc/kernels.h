@@ -41,7 +41,9 @@ struct PrepParams {
     int mcm_rows;             // observations averaged (min(n, available), :112)
     const double* prior_n;    // [W] injected conjugate_prior_n (nullptr: from the MCM series)
     const double* rf_row;     // [D] risk-free forward-filled onto the daily rows
-    const int* day_row;       // [W]
+    const int* day_row;       // [W] last shared return row of the window (the trade date's row for daily windows)
+    const int* extra_row;     // [W] per-date last return row of resampled (weekly) windows, or nullptr
+    const int* caps_row;      // [W] row of the trade date in the caps matrix, or nullptr (= day_row)
     const int* span_days;     // [W]
     const int* hf_row0;       // [W] first intraday RETURN row of the HF window (= first price row + 1)
     const int* hf_m;          // [W] number of HF returns m
@@ -138,6 +140,8 @@ struct LoopParams {
 };
 cudaError_t launch_backtest_loop(const LoopParams& p, cudaStream_t st);
 
+void launch_gather_log_returns(const double* P, int ld_in, const int* num, const int* den, double* out, int ld_out,
+                               int rows, int n_assets, cudaStream_t st);
 void launch_fetch_ints(const int* src_host, int* dst, long long n, cudaStream_t st);
 void launch_excess_returns(const double* lr, int ld, const double* rf_row, int day_row, int span_days, int n_window,
                            int N, double* X, cudaStream_t st);

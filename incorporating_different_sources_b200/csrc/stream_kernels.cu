@@ -138,7 +138,12 @@ __global__ void __launch_bounds__(PREP_THREADS) window_prep_kernel(PrepParams p)
     const int tid = threadIdx.x;
     const int N = p.n_assets;
     const int day_row = p.day_row[w];
-    const long long r0 = (long long)day_row - K + 1;   // first return row of the window
+    // resampled (weekly) windows: the last return of the window is a per-date row (price at d against the
+    // previous week's close) stored apart from the shared weekly rows; K1 shared rows + 1 extra row
+    const int extra_row = p.extra_row ? p.extra_row[w] : -1;
+    const int K1 = extra_row >= 0 ? K - 1 : K;
+    const long long r0 = (long long)day_row - K1 + 1;  // first (shared) return row of the window
+    const int caps_row = p.caps_row ? p.caps_row[w] : day_row;
     double* scal = p.scal + (long long)w * BP_S_COUNT;
 
     // ---- a_k = (1 + rf)^(gbar/365) - 1  (:40-48); gbar = calendar span / (n-1)
@@ -146,7 +151,8 @@ __global__ void __launch_bounds__(PREP_THREADS) window_prep_kernel(PrepParams p)
     const double expo = gbar / 365.0;
     double sa = 0.0, saa = 0.0;
     for (int k = tid; k < K; k += PREP_THREADS) {
-        const double a = pow(1.0 + p.rf_row[r0 + k], expo) - 1.0;
+        const long long rr = k < K1 ? r0 + k : (long long)extra_row;
+        const double a = pow(1.0 + p.rf_row[rr], expo) - 1.0;
         a_s[k] = a;
         sa += a;
         saa = fma(a, a, saa);
@@ -157,10 +163,17 @@ __global__ void __launch_bounds__(PREP_THREADS) window_prep_kernel(PrepParams p)
     double2 sum[NCH], wsum[NCH];
     // ---- daily column sums: t = L'1 - (sum a),  p = L'a - (a'a)/2
     for (int col0 = 0; col0 < p.ldv; col0 += 512) {
-        col_accumulate<false>(p.lr_daily, p.ld, r0, K, col0, a_s, nullptr, nullptr, false, sum, wsum);
-        const double2 ts = reduce_cols(sum, red);
-        const double2 us = reduce_cols(wsum, red);
+        col_accumulate<false>(p.lr_daily, p.ld, r0, K1, col0, a_s, nullptr, nullptr, false, sum, wsum);
+        double2 ts = reduce_cols(sum, red);
+        double2 us = reduce_cols(wsum, red);
         const int c = col0 + tid * 2;
+        if (c < p.ldv && extra_row >= 0) {
+            const double2 x = *reinterpret_cast<const double2*>(p.lr_daily + (long long)extra_row * p.ld + c);
+            ts.x += x.x;
+            ts.y += x.y;
+            us.x = fma(a_s[K1], x.x, us.x);
+            us.y = fma(a_s[K1], x.y, us.y);
+        }
         if (c < p.ldv) {
             double2 tv = make_double2(c < N ? ts.x - sa : 0.0, c + 1 < N ? ts.y - sa : 0.0);
             double2 pv = make_double2(c < N ? us.x - 0.5 * saa : 0.0, c + 1 < N ? us.y - 0.5 * saa : 0.0);
@@ -194,10 +207,13 @@ __global__ void __launch_bounds__(PREP_THREADS) window_prep_kernel(PrepParams p)
         const double* mcm = p.mcm;
         const int rows = p.mcm_rows;          // min(n, available observations): iloc[-n:] semantics (:112)
         double ms = 0.0;
-        for (int k = tid; k < rows; k += PREP_THREADS) ms += mcm[day_row - rows + 1 + k];
+        // resampled windows: rows-1 shared (weekly) observations ending at day_row + the value at the trade date
+        const int shared = extra_row >= 0 ? rows - 1 : rows;
+        for (int k = tid; k < shared; k += PREP_THREADS) ms += mcm[day_row - shared + 1 + k];
         ms = block_sum(ms, scratch);
+        const double cur = mcm[extra_row >= 0 ? extra_row : day_row];
+        if (extra_row >= 0) ms += cur;
         avg = ms / (double)rows;
-        const double cur = mcm[day_row];
         const double frac = cur > avg ? cur / avg : avg / cur;
         n0 = (double)p.n_window * frac * p.mcm_scaling;
     }
@@ -206,12 +222,12 @@ __global__ void __launch_bounds__(PREP_THREADS) window_prep_kernel(PrepParams p)
     // ---- prior weights w0 (:679-701 value weighted, :661-677 equally weighted)
     double cs = 0.0;
     if (p.prior_kind == BP_PRIOR_VW) {
-        for (int j = tid; j < N; j += PREP_THREADS) cs += p.caps[(long long)day_row * p.ld_caps + j];
+        for (int j = tid; j < N; j += PREP_THREADS) cs += p.caps[(long long)caps_row * p.ld_caps + j];
         cs = block_sum(cs, scratch);
     }
     for (int j = tid; j < p.ldv; j += PREP_THREADS) {
         double v = 0.0;
-        if (j < N) v = p.prior_kind == BP_PRIOR_VW ? p.caps[(long long)day_row * p.ld_caps + j] / cs : 1.0 / (double)N;
+        if (j < N) v = p.prior_kind == BP_PRIOR_VW ? p.caps[(long long)caps_row * p.ld_caps + j] / cs : 1.0 / (double)N;
         w0_s[j] = v;
         p.w0[(long long)w * p.ldv + j] = v;
     }
@@ -330,6 +346,29 @@ void launch_unpack_vec(const double* v, int ldv, int N, long long W, double* out
     long long blocks = (total + 255) / 256;
     if (blocks > 4096) blocks = 4096;
     unpack_vec_kernel<<<(unsigned)blocks, 256, 0, st>>>(v, ldv, N, W, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Resampled (weekly) windows (:106, :153): out[i] = ln(P[num[i]] / P[den[i]]) for arbitrary row pairs of the
+// dense daily price matrix: one row per week (week close against the previous week's close) followed by one
+// row per trading date (price at d against the previous week's close).  num == den gives a zero row.
+__global__ void gather_log_returns_kernel(const double* __restrict__ P, int ld_in, const int* __restrict__ num,
+                                          const int* __restrict__ den, double* __restrict__ out, int ld_out,
+                                          int rows, int n_assets) {
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const double* pn = P + (long long)num[r] * ld_in;
+        const double* pd = P + (long long)den[r] * ld_in;
+        const bool zero = num[r] == den[r];
+        for (int c = threadIdx.x; c < ld_out; c += blockDim.x)
+            out[(long long)r * ld_out + c] = (c < n_assets && !zero) ? log(pn[c] / pd[c]) : 0.0;
+    }
+}
+
+void launch_gather_log_returns(const double* P, int ld_in, const int* num, const int* den, double* out, int ld_out,
+                               int rows, int n_assets, cudaStream_t st) {
+    if (rows <= 0) return;
+    const int blocks = rows < 4096 ? rows : 4096;
+    gather_log_returns_kernel<<<blocks, 128, 0, st>>>(P, ld_in, num, den, out, ld_out, rows, n_assets);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -187,6 +187,23 @@ class BayesEngine:
         self.n_assets, self.n_days, self.n_hf_rows = N, D, int(desc.n_hf_rows)
         self._inflight = keep if async_copy else None
 
+    def set_resampled(self, rows):
+        """Build the weekly return rows (:class:`~.windows.ResampledRows`) on the device from the resident prices."""
+        num = np.ascontiguousarray(rows.num_row, dtype=np.int32)
+        den = np.ascontiguousarray(rows.den_row, dtype=np.int32)
+        rf = _c64(rows.rf_row)
+        r = _lib.ResampledDesc()
+        r.n_rows = int(num.shape[0])
+        r.num_row, r.den_row, r.rf_row = num.ctypes.data, den.ctypes.data, rf.ctypes.data
+        mcm = None
+        r.mcm = None
+        if rows.mcm is not None:
+            mcm = _c64(rows.mcm)
+            r.mcm = mcm.ctypes.data
+        rc = self._lib.bp_set_resampled(self._h, C.byref(r))
+        if rc:
+            _raise(rc)
+
     def prepare_market(self):
         """Re-run the on-device log-return stage (used to time the whole device path)."""
         rc = self._lib.bp_prepare_market(self._h)
@@ -217,6 +234,14 @@ class BayesEngine:
         d.risk_aversion = float(b.risk_aversion)
         d.prior_weights = int(b.prior_weights)
         d.mcm_rows = int(getattr(b, "mcm_rows", 0) or 0)
+        d.resampled = int(bool(getattr(b, "resampled", False)))
+        d.extra_row = None
+        d.caps_row = None
+        if d.resampled:
+            for name in ("extra_row", "caps_row"):
+                a = np.ascontiguousarray(getattr(b, name), dtype=np.int32)
+                keep.append(a)
+                setattr(d, name, a.ctypes.data)
         d.prior_n = None
         if getattr(b, "prior_n", None) is not None:
             pn = np.ascontiguousarray(b.prior_n, dtype=np.float64)

@@ -31,6 +31,9 @@ class WindowBatch:
     prior_weights: int = 0       # 0 value weighted, 1 equally weighted
     mcm_rows: int = 0            # MCM observations averaged (0 = rolling_window)
     prior_n: Optional[np.ndarray] = None   # injected conjugate_prior_n per window
+    resampled: bool = False      # weekly windows: rows refer to the ResampledRows of plan_weekly_windows
+    extra_row: Optional[np.ndarray] = None   # int32 [W] per-date last return row (weekly windows)
+    caps_row: Optional[np.ndarray] = None    # int32 [W] daily row of the trade date (weekly windows)
 
     @property
     def n_windows(self) -> int:
@@ -109,6 +112,83 @@ def plan_daily_windows(spec, dates: np.ndarray, d_indices: Sequence[int], hf_ts:
         risk_aversion=float(spec["risk_aversion"]) if spec.get("risk_aversion") is not None else 1.0,
         prior_weights=prior_kind_of(strat) if conj else 0,
     )
+
+
+@dataclass
+class ResampledRows:
+    """Return rows of weekly windows, built on the device from the daily prices (``bp_set_resampled``):
+    row i = ln(P[num_row[i]] / P[den_row[i]]).  Rows 0..n_weeks-1: week close against the previous week's close
+    (``resample('W').last()``, :153); rows n_weeks..n_weeks+D-1: price at trading date d against the previous
+    week's close (the partial last week of a window).  ``rf_row`` / ``mcm`` carry the risk-free rate forward-filled
+    at each row's Sunday label (:54 — including the look-ahead of the partial week's label) and the MCM value."""
+    num_row: np.ndarray
+    den_row: np.ndarray
+    rf_row: np.ndarray
+    mcm: Optional[np.ndarray]
+    n_weeks: int
+
+
+def week_ids(dates: np.ndarray) -> np.ndarray:
+    """Bucket of ``resample('W')`` (weeks end on Sunday; 1970-01-01 is a Thursday)."""
+    return (dates.astype("datetime64[D]").astype(np.int64) + 3) // 7
+
+
+def plan_weekly_windows(spec, dates: np.ndarray, d_indices: Sequence[int], rf_dates: np.ndarray, rf_values: np.ndarray,
+                        mcm: Optional[np.ndarray] = None, hf_ts: Optional[np.ndarray] = None,
+                        hf_lookback_days: Optional[int] = None, need_hf: bool = True):
+    """Window descriptors for ``rolling_window_frequency == 'weekly'`` (:104-106, :151-153).
+
+    A window at date d holds the closes of the n-1 complete weeks before d's week plus the price at d; its n-1
+    returns are n-2 shared weekly rows and one per-date row.  Returns (ResampledRows, WindowBatch).
+    """
+    n = int(spec["rolling_window"])
+    D = len(dates)
+    wid = week_ids(dates)
+    if np.any(np.diff(wid) > 1):
+        raise NotImplementedError("empty week in resample('W'): the reference would emit a NaN row")
+    wk = wid - wid[0]                                   # week index of every trading date
+    n_weeks = int(wk[-1]) + 1
+    last = np.r_[np.nonzero(np.diff(wk))[0], D - 1]     # last trading row of every week
+    prev_close = np.where(wk >= 1, last[np.maximum(wk - 1, 0)], np.arange(D))
+    num = np.r_[last, np.arange(D)].astype(np.int32)
+    den = np.r_[np.r_[last[0], last[:-1]], prev_close].astype(np.int32)
+    labels = ((wid[0] + np.arange(n_weeks)) * 7 + 3).astype("datetime64[D]").astype("datetime64[ns]")   # Sundays
+    rf_week = ffill_rows(labels, rf_dates, rf_values)
+    rf_row = np.r_[rf_week, rf_week[wk]]
+    mcm_rows = None
+    if mcm is not None:
+        mcm = np.atleast_2d(np.asarray(mcm, dtype=np.float64))
+        mcm_rows = np.concatenate([mcm[:, last], mcm], axis=1)
+    rows = ResampledRows(num, den, rf_row.astype(np.float64), mcm_rows, n_weeks)
+
+    d_idx = np.asarray(d_indices, dtype=np.int64)
+    k = wk[d_idx]
+    if k.min() < n - 1:
+        raise ValueError(f"a weekly window of {n} prices needs {n - 1} complete weeks before the trade date")
+    hf_lo = hf_hi = None
+    if need_hf:
+        if hf_ts is None:
+            raise ValueError("intraday timestamps required for the conjugate prior")
+        Dd = hf_lookback(spec, hf_lookback_days)
+        dd = dates[d_idx]
+        hf_lo = np.searchsorted(hf_ts, dd - Dd * _DAY + _DAY, side="right").astype(np.int32)
+        hf_hi = np.searchsorted(hf_ts, dd + _DAY, side="right").astype(np.int32)
+    strat = spec["weighting_strategy"]
+    conj = strat.startswith("conjugate")
+    batch = WindowBatch(
+        rolling_window=n,
+        day_row=(k - 1).astype(np.int32),                              # last shared weekly row
+        span_days=np.full(len(d_idx), 7 * (n - 1), dtype=np.int32),    # labels are consecutive Sundays
+        hf_lo=hf_lo, hf_hi=hf_hi,
+        mcm_index=mcm_index_of(strat) if conj else 0,
+        mcm_scaling=float(spec["mcm_scaling"]) if conj and spec.get("mcm_scaling") is not None else 1.0,
+        risk_aversion=float(spec["risk_aversion"]) if spec.get("risk_aversion") is not None else 1.0,
+        prior_weights=prior_kind_of(strat) if conj else 0,
+        resampled=True,
+        extra_row=(n_weeks + d_idx).astype(np.int32),
+        caps_row=d_idx.astype(np.int32),
+    )
+    return rows, batch
 
 
 def ffill_rows(target_dates: np.ndarray, src_dates: np.ndarray, src_values: np.ndarray) -> np.ndarray:

@@ -32,6 +32,9 @@ CASES = [
     dict(name="bt_conj_epu_ew_weekly_top6of10", market=dict(n_assets=10, n_days=100, seed=3003),
          spec=spec(weighting_strategy="conjugate_hf_epu_ew", size=6, rolling_window=50, rebalancing_frequency="weekly",
                    risk_aversion=3, turnover_cost=5, display_name="Conjugate HF-EPU EW"), start=-30, end=-1),
+    dict(name="bt_conj_weeklywin_monthly_n7", market=dict(n_assets=7, n_days=330, seed=3005),
+         spec=spec(size=7, rolling_window=40, rolling_window_frequency="weekly", rebalancing_frequency="monthly"),
+         start=-70, end=-2),
     dict(name="bt_vw_daily_top5of9", market=dict(n_assets=9, n_days=60, seed=3004),
          spec=spec(weighting_strategy="vw", size=5, risk_aversion=None, mcm_scaling=None, rolling_window=20,
                    display_name="VW"), start=-15, end=-1),

@@ -31,9 +31,8 @@ def _daily(meta):
 def test_gpu_matches_reference_golden(engine, name):
     from incorporating_different_sources_b200.engine import upload_synthetic
     from incorporating_different_sources_b200.windows import plan_daily_windows
+    from incorporating_different_sources_b200.windows import plan_weekly_windows
     z, meta = load_golden(name)
-    if not _daily(meta):
-        pytest.skip("weekly windows: batched engine is daily-only; covered per window by test_gpu_facade.py")
     mkt = market_for(meta)
     spec = meta["spec"]
     conj = spec["weighting_strategy"].startswith("conjugate")
@@ -42,8 +41,14 @@ def test_gpu_matches_reference_golden(engine, name):
         d_idx = w["d_idx"]
         cols = z[pre + "cols"]
         upload_synthetic(engine, mkt, cols=cols)
-        batch = plan_daily_windows(spec, mkt.dates, [d_idx], mkt.hf_ts, hf_lookback_days=meta["hf_days"],
-                                   need_hf=conj)
+        if _daily(meta):
+            batch = plan_daily_windows(spec, mkt.dates, [d_idx], mkt.hf_ts, hf_lookback_days=meta["hf_days"],
+                                       need_hf=conj)
+        else:
+            rows, batch = plan_weekly_windows(spec, mkt.dates, [d_idx], mkt.dates, mkt.rf,
+                                              np.stack([mkt.vix, mkt.epu]), mkt.hf_ts,
+                                              hf_lookback_days=meta["hf_days"], need_hf=conj)
+            engine.set_resampled(rows)
         if conj:
             got = engine.conjugate(batch, outputs=("weights", "nu", "w1", "t", "w0", "scalars", "status", "T", "S0", "S1"))
             assert got["status"][0] == 0
@@ -227,4 +232,35 @@ def test_gpu_window_overlap_reuse_matches_oracle(engine, dates):
             assert relerr(got[k][i], ref[k]) <= TOL, (k, i)
         refj = bo.jeffreys_window(jspec, mkt, d_idx[i], cols)
         assert relerr(gotj["T"][i], refj["T"]) <= TOL
+        assert relerr(gotj["weights"][i], refj["weights"]) <= TOL
+
+
+@pytest.mark.parametrize("n_windows", [6, 40])
+def test_gpu_weekly_batched_matches_oracle(engine, n_windows):
+    """Weekly windows (the reference's shipped configuration: resample('W').last(), :151-153) in the batched
+    engine: shared weekly return rows + one per-date row, for conjugate and Jeffreys."""
+    from incorporating_different_sources_b200.engine import upload_synthetic
+    from incorporating_different_sources_b200.synthetic import generate_market
+    from incorporating_different_sources_b200.windows import plan_weekly_windows
+    n = 20
+    mkt = generate_market(n, 460, seed=1234)
+    spec = dict(weighting_strategy="conjugate_hf_epu_vw", size=n, risk_aversion=5, rolling_window=70,
+                rolling_window_frequency="weekly", mcm_scaling=2)
+    jspec = dict(spec, weighting_strategy="jeffreys")
+    d_idx = list(range(460 - n_windows, 460))
+    cols = np.arange(n)
+    upload_synthetic(engine, mkt)
+    rows, cb = plan_weekly_windows(spec, mkt.dates, d_idx, mkt.dates, mkt.rf, np.stack([mkt.vix, mkt.epu]), mkt.hf_ts)
+    engine.set_resampled(rows)
+    got = engine.conjugate(cb, outputs=("weights", "t", "scalars", "status", "T", "S1"))
+    _, jb = plan_weekly_windows(jspec, mkt.dates, d_idx, mkt.dates, mkt.rf, None, need_hf=False)
+    gotj = engine.jeffreys(jb, outputs=("weights", "status"))
+    assert not got["status"].any() and not gotj["status"].any()
+    for i, d in enumerate(d_idx):
+        ref = bo.conjugate_window(spec, mkt, d, cols)
+        assert relerr(got["t"][i], ref["t"]) <= TOL and relerr(got["T"][i], ref["T"]) <= TOL
+        assert abs(got["scalars"][i][0] - ref["n0"]) <= TOL * ref["n0"]
+        assert relerr(got["S1"][i], ref["S1"]) <= TOL
+        assert relerr(got["weights"][i], ref["weights"]) <= TOL
+        refj = bo.jeffreys_window(jspec, mkt, d, cols)
         assert relerr(gotj["weights"][i], refj["weights"]) <= TOL
