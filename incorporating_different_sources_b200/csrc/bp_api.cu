@@ -81,8 +81,8 @@ struct bp_handle {
     int* desc_host = nullptr;          // page-locked staging of the descriptors (read zero-copy by a kernel)
     size_t desc_cap = 0;               // capacity in ints
     // block tile stores of the Gram kernel (window-overlap reuse) and the smallest batch that uses them
-    double* store[2] = {nullptr, nullptr};
-    size_t store_cap[2] = {0, 0};      // capacity in doubles
+    double* store[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [phase][level]
+    size_t store_cap[2][2] = {{0, 0}, {0, 0}};                           // capacity in doubles
     int reuse_min_windows = 32;
     // work counters of the Gram stage since the last bp_get_gram_work (bench.py's roofline accounting)
     double work_k_rows = 0, work_add_blocks = 0, work_pre_rows = 0, work_full_rows = 0;
@@ -256,32 +256,79 @@ struct Batch {
     bool resampled = false;
     const int *extra_row = nullptr, *caps_row = nullptr;
     const int* gdesc = nullptr;        // [W][GRAM_DESC_INTS] Gram job descriptors
-    const int* bdesc[2] = {nullptr, nullptr};   // descriptors of the block precompute launches (phase A / B)
-    int nblocks[2] = {0, 0};
+    const int* bdesc[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // block precompute launches [phase][level]
+    int nblocks[2][2] = {{0, 0}, {0, 0}};
 };
 
-// Block grid of one phase: block b covers return rows [off + b*blk, off + (b+1)*blk); blk == 0: no reuse
+// Block grids of one phase, two levels (0 = coarse, 1 = fine; the fine size divides the coarse size): block b of
+// level l covers return rows [off + b*blk[l], off + (b+1)*blk[l]); blk[l] == 0: level unused
 struct PhasePlan {
-    int blk = 0, off = 0, bmin = 0, nb = 0;
+    int blk[2] = {0, 0};
+    int off = 0;
+    int bmin[2] = {0, 0}, nb[2] = {0, 0};
 };
 
 inline long long floor_div(long long a, long long b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
-// split the row range [row0, row0+rows) of a window on the block grid: d[0..5] = head K segment, tail K
-// segment, first block (relative to bmin) and block count
-void plan_phase(int row0, int rows, const PhasePlan& P, int* d, int* b_lo_out = nullptr, int* b_hi_out = nullptr) {
-    d[0] = row0; d[1] = rows; d[2] = 0; d[3] = 0; d[4] = 0; d[5] = 0;
-    if (P.blk <= 0 || rows <= 0) return;
+// Split of the row range [row0, row0+rows) of a window: head rows, fine blocks, coarse blocks, fine blocks, tail rows
+struct Split {
+    long long k0_row = 0, k0_n = 0, k1_row = 0, k1_n = 0;     // rows contracted on the tensor cores
+    long long c_lo = 0, c_hi = 0;                             // coarse blocks [c_lo, c_hi)
+    long long fa_lo = 0, fa_hi = 0, fb_lo = 0, fb_hi = 0;     // fine blocks on the head / tail side
+};
+
+Split split_rows(int row0, int rows, const PhasePlan& P) {
+    Split s;
+    s.k0_row = row0;
+    s.k0_n = rows;
+    if (rows <= 0 || (P.blk[0] <= 0 && P.blk[1] <= 0)) return s;
     const long long r0 = (long long)row0 - P.off, r1 = r0 + rows;
-    const long long b_lo = floor_div(r0 + P.blk - 1, P.blk), b_hi = floor_div(r1, P.blk);
-    if (b_hi <= b_lo) return;
-    d[1] = (int)(b_lo * P.blk - r0);                 // head rows before the first whole block
-    d[2] = (int)(P.off + b_hi * P.blk);              // tail rows after the last whole block
-    d[3] = (int)(r1 - b_hi * P.blk);
-    d[4] = (int)(b_lo - P.bmin);
-    d[5] = (int)(b_hi - b_lo);
-    if (b_lo_out) *b_lo_out = (int)b_lo;
-    if (b_hi_out) *b_hi_out = (int)b_hi;
+    long long head_end = r1, tail_begin = r1;      // relative rows; head = [r0, head_end), tail = [tail_begin, r1)
+    if (P.blk[0] > 0) {
+        const long long B = P.blk[0];
+        const long long lo = floor_div(r0 + B - 1, B), hi = floor_div(r1, B);
+        if (hi > lo) {
+            s.c_lo = lo;
+            s.c_hi = hi;
+            head_end = lo * B;
+            tail_begin = hi * B;
+        }
+    }
+    if (P.blk[1] > 0) {
+        const long long F = P.blk[1];
+        if (s.c_hi > s.c_lo) {
+            const long long f_lo = floor_div(r0 + F - 1, F), f_hi = floor_div(r1, F);
+            s.fa_lo = f_lo;  s.fa_hi = head_end / F;          // head_end is a multiple of the coarse (hence fine) size
+            s.fb_lo = tail_begin / F;  s.fb_hi = f_hi;
+            s.k0_n = f_lo * F - r0;
+            s.k1_row = P.off + f_hi * F;
+            s.k1_n = r1 - f_hi * F;
+        } else {
+            const long long f_lo = floor_div(r0 + F - 1, F), f_hi = floor_div(r1, F);
+            if (f_hi > f_lo) {
+                s.fa_lo = f_lo;  s.fa_hi = f_hi;
+                s.k0_n = f_lo * F - r0;
+                s.k1_row = P.off + f_hi * F;
+                s.k1_n = r1 - f_hi * F;
+            }
+        }
+    } else if (s.c_hi > s.c_lo) {
+        s.k0_n = head_end - r0;
+        s.k1_row = P.off + tail_begin;
+        s.k1_n = r1 - tail_begin;
+    }
+    return s;
+}
+
+// descriptor ints of one phase (GRAM_PHASE_INTS) from a split, block indices relative to the stores
+void write_phase_desc(const Split& s, const PhasePlan& P, int* d) {
+    d[0] = (int)s.k0_row; d[1] = (int)s.k0_n; d[2] = (int)s.k1_row; d[3] = (int)s.k1_n;
+    d[4] = (int)(s.c_lo - P.bmin[0]);  d[5] = (int)(s.c_hi - s.c_lo);
+    d[6] = (int)(s.fa_lo - P.bmin[1]); d[7] = (int)(s.fa_hi - s.fa_lo);
+    d[8] = (int)(s.fb_lo - P.bmin[1]); d[9] = (int)(s.fb_hi - s.fb_lo);
+    if (d[5] == 0) d[4] = 0;
+    if (d[7] == 0) d[6] = 0;
+    if (d[9] == 0) d[8] = 0;
 }
 
 int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* out) {
@@ -310,8 +357,14 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
     PhasePlan plan[2];
     if (W >= h->reuse_min_windows) {
         const int K = n - 1;
-        plan[1].blk = K >= 512 ? 128 : 64;
-        if (K < 2 * plan[1].blk || rs) plan[1].blk = 0;      // resampled windows: shared rows + one per-date row, no block reuse
+        if (!rs) {          // resampled windows: shared weekly rows + one per-date row, no block reuse
+            // Block sizes were tuned on the bench workload (N = 500): coarse/fine 128/32 for the 1007-row Jeffreys
+            // window and 64/16 for the 251-row conjugate window gave 18.6 ms for the Gram stage, 512/64 + 128/32
+            // 19.4 ms, a single level (128 / 64) 21.9 ms; neither the DMMA pipe (40-50 %) nor L2 (26-32 %) is
+            // saturated then, the stage is bound by per-item latencies.
+            if (K >= 512) { plan[1].blk[0] = 128; plan[1].blk[1] = 32; }
+            else if (K >= 128) { plan[1].blk[0] = 64; plan[1].blk[1] = 16; }
+        }
         if (need_hf) {
             // regular intraday calendar: every window has the same number of rows and consecutive windows
             // advance by a constant stride that divides it -> one block per stride (a trading day of bars)
@@ -321,39 +374,52 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             for (int w = 0; regular && w < W; ++w)
                 regular = b->hf_hi[w] - b->hf_lo[w] == H0 && (b->hf_lo[w] - b->hf_lo[0]) % stride == 0;
             if (regular) {
-                plan[0].blk = stride;
+                plan[0].blk[0] = stride;
                 plan[0].off = b->hf_lo[0] % stride;
             } else if (H0 >= 3 * 64) {
-                plan[0].blk = 64;
+                plan[0].blk[0] = 64;
+                plan[0].blk[1] = 16;
             }
         }
     }
-    // first pass: block ranges touched by the windows
+    auto phase_rows = [&](int ph, int w, int& row0, int& rows) {
+        row0 = ph == 0 ? b->hf_lo[w] + 1 : b->day_row[w] - n + 2;
+        rows = ph == 0 ? b->hf_hi[w] - b->hf_lo[w] - 1 : n - 1;
+    };
+    // first pass: block ranges touched by the windows, per level
     for (int ph = 0; ph < 2; ++ph) {
-        if (plan[ph].blk <= 0) continue;
-        long long bmin = (1LL << 40), bmax = -(1LL << 40);
+        if (plan[ph].blk[0] <= 0 && plan[ph].blk[1] <= 0) continue;
+        if (ph == 0 && !need_hf) { plan[ph] = PhasePlan(); continue; }
+        long long lo[2] = {1LL << 40, 1LL << 40}, hi[2] = {-(1LL << 40), -(1LL << 40)};
         for (int w = 0; w < W; ++w) {
-            int d6[6], lo = 0, hi = 0;
-            const int row0 = ph == 0 ? b->hf_lo[w] + 1 : b->day_row[w] - n + 2;
-            const int rows = ph == 0 ? b->hf_hi[w] - b->hf_lo[w] - 1 : n - 1;
-            plan_phase(row0, rows, plan[ph], d6, &lo, &hi);
-            if (d6[5] > 0) { bmin = std::min<long long>(bmin, lo); bmax = std::max<long long>(bmax, hi); }
+            int row0, rows;
+            phase_rows(ph, w, row0, rows);
+            const Split sp = split_rows(row0, rows, plan[ph]);
+            if (sp.c_hi > sp.c_lo) { lo[0] = std::min(lo[0], sp.c_lo); hi[0] = std::max(hi[0], sp.c_hi); }
+            if (sp.fa_hi > sp.fa_lo) { lo[1] = std::min(lo[1], sp.fa_lo); hi[1] = std::max(hi[1], sp.fa_hi); }
+            if (sp.fb_hi > sp.fb_lo) { lo[1] = std::min(lo[1], sp.fb_lo); hi[1] = std::max(hi[1], sp.fb_hi); }
         }
-        if (bmax <= bmin) { plan[ph].blk = 0; continue; }
-        plan[ph].bmin = (int)bmin;
-        plan[ph].nb = (int)(bmax - bmin);
-        const size_t need = (size_t)plan[ph].nb * npairs_t * GRAM_BLOCK_TILE_DOUBLES;
-        if (need * sizeof(double) > h->ws_limit / 2) { plan[ph].blk = 0; plan[ph].nb = 0; continue; }   // too big: no reuse
-        if (need > h->store_cap[ph]) {
-            CU_TRY(cudaStreamSynchronize(h->stream));
-            cudaFree(h->store[ph]);
-            h->store[ph] = nullptr;
-            h->store_cap[ph] = 0;
-            CU_TRY(cudaMalloc(&h->store[ph], need * sizeof(double)));
-            h->store_cap[ph] = need;
+        for (int l = 0; l < 2; ++l) {
+            if (hi[l] <= lo[l]) { plan[ph].blk[l] = 0; plan[ph].nb[l] = 0; continue; }
+            plan[ph].bmin[l] = (int)lo[l];
+            plan[ph].nb[l] = (int)(hi[l] - lo[l]);
+            const size_t need = (size_t)plan[ph].nb[l] * npairs_t * GRAM_BLOCK_TILE_DOUBLES;
+            if (need * sizeof(double) > h->ws_limit / 2) {      // too big: give up the reuse of this phase
+                plan[ph] = PhasePlan();
+                break;
+            }
+            if (need > h->store_cap[ph][l]) {
+                CU_TRY(cudaStreamSynchronize(h->stream));
+                cudaFree(h->store[ph][l]);
+                h->store[ph][l] = nullptr;
+                h->store_cap[ph][l] = 0;
+                CU_TRY(cudaMalloc(&h->store[ph][l], need * sizeof(double)));
+                h->store_cap[ph][l] = need;
+            }
         }
     }
-    const size_t ints_needed = (size_t)(7 + GRAM_DESC_INTS) * W + (size_t)GRAM_DESC_INTS * (plan[0].nb + plan[1].nb);
+    const int nb_total = plan[0].nb[0] + plan[0].nb[1] + plan[1].nb[0] + plan[1].nb[1];
+    const size_t ints_needed = (size_t)(7 + GRAM_DESC_INTS) * W + (size_t)GRAM_DESC_INTS * nb_total;
     if (ints_needed > h->desc_cap) {
         if (h->desc) {
             CU_TRY(cudaStreamSynchronize(h->stream));
@@ -401,34 +467,39 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             host[(size_t)3 * W + w] = lo + 1;        // first HF return row: the window's first bar has no return (F5)
             host[(size_t)4 * W + w] = m;
             max_m = std::max(max_m, m);
-            plan_phase(lo + 1, m, plan[0], gd + (size_t)w * GRAM_DESC_INTS);
+            write_phase_desc(split_rows(lo + 1, m, plan[0]), plan[0], gd + (size_t)w * GRAM_DESC_INTS);
         }
         if (rs) {
-            int* d6 = gd + (size_t)w * GRAM_DESC_INTS + 6;
-            d6[0] = dr - (n - 2) + 1; d6[1] = n - 2;       // shared weekly rows
-            d6[2] = b->extra_row[w];  d6[3] = 1;           // the trade date's own row
+            int* dB = gd + (size_t)w * GRAM_DESC_INTS + GRAM_PHASE_INTS;
+            dB[0] = dr - (n - 2) + 1; dB[1] = n - 2;       // shared weekly rows
+            dB[2] = b->extra_row[w];  dB[3] = 1;           // the trade date's own row
         } else {
-            plan_phase(dr - n + 2, n - 1, plan[1], gd + (size_t)w * GRAM_DESC_INTS + 6);
+            write_phase_desc(split_rows(dr - n + 2, n - 1, plan[1]), plan[1], gd + (size_t)w * GRAM_DESC_INTS + GRAM_PHASE_INTS);
         }
         const int* d = gd + (size_t)w * GRAM_DESC_INTS;
         auto r8 = [](int r) { return (r + 7) / 8 * 8; };
-        h->work_k_rows += r8(d[1]) + r8(d[3]) + r8(d[7]) + r8(d[9]);
-        h->work_add_blocks += d[5] + d[11];
+        for (int ph = 0; ph < 2; ++ph) {
+            const int* dp = d + ph * GRAM_PHASE_INTS;
+            h->work_k_rows += r8(dp[1]) + r8(dp[3]);
+            h->work_add_blocks += dp[5] + dp[7] + dp[9];
+        }
         h->work_full_rows += (need_hf ? b->hf_hi[w] - b->hf_lo[w] - 1 : 0) + (n - 1);
     }
-    h->work_pre_rows += (double)plan[0].nb * ((plan[0].blk + 7) / 8 * 8) + (double)plan[1].nb * ((plan[1].blk + 7) / 8 * 8);
+    for (int ph = 0; ph < 2; ++ph)
+        for (int l = 0; l < 2; ++l) h->work_pre_rows += (double)plan[ph].nb[l] * ((plan[ph].blk[l] + 7) / 8 * 8);
     // descriptors of the block precompute launches: one pseudo-window per block, rows of that block only
     int* bd = gd + (size_t)W * GRAM_DESC_INTS;
-    for (int ph = 0; ph < 2; ++ph) {
-        for (int k = 0; k < plan[ph].nb; ++k) {
-            int* d = bd + (size_t)k * GRAM_DESC_INTS + 6 * ph;
-            d[0] = plan[ph].off + (plan[ph].bmin + k) * plan[ph].blk;
-            d[1] = plan[ph].blk;
+    for (int ph = 0; ph < 2; ++ph)
+        for (int l = 0; l < 2; ++l) {
+            for (int k = 0; k < plan[ph].nb[l]; ++k) {
+                int* d = bd + (size_t)k * GRAM_DESC_INTS + GRAM_PHASE_INTS * ph;
+                d[0] = plan[ph].off + (plan[ph].bmin[l] + k) * plan[ph].blk[l];
+                d[1] = plan[ph].blk[l];
+            }
+            out->bdesc[ph][l] = plan[ph].nb[l] ? h->desc + (bd - host) : nullptr;
+            out->nblocks[ph][l] = plan[ph].nb[l];
+            bd += (size_t)plan[ph].nb[l] * GRAM_DESC_INTS;
         }
-        out->bdesc[ph] = plan[ph].nb ? h->desc + (bd - host) : nullptr;
-        out->nblocks[ph] = plan[ph].nb;
-        bd += (size_t)plan[ph].nb * GRAM_DESC_INTS;
-    }
     out->gdesc = h->desc + (size_t)7 * W;
     out->resampled = rs;
     out->extra_row = rs ? h->desc + 5 * (size_t)W : nullptr;
@@ -555,8 +626,8 @@ GramParams gram_params(const bp_handle* h, const Batch& B, const Layout& L, cons
     g.scal = c.scal;
     g.out = c.S;
     g.desc = B.gdesc + (size_t)w0 * GRAM_DESC_INTS;
-    g.storeA = h->store[0];
-    g.storeB = h->store[1];
+    for (int a = 0; a < 2; ++a)
+        for (int l = 0; l < 2; ++l) g.store[a][l] = h->store[a][l];
     const bool hf = kind == GRAM_S0 || kind == GRAM_S1;
     const bool daily = kind != GRAM_S0;
     g.use_phaseA = hf;
@@ -574,20 +645,22 @@ GramParams gram_params(const bp_handle* h, const Batch& B, const Layout& L, cons
     return g;
 }
 
-// block precompute: the Gram tile of every whole block of a phase, written fragment-major into the store
+// block precompute: the Gram tile of every whole block of a phase / level, written fragment-major into its store
 int run_block_precompute(bp_handle* h, const Batch& B, int ph) {
-    if (B.nblocks[ph] <= 0) return BP_OK;
-    GramParams g{};
-    g.n_windows = B.nblocks[ph];
-    g.n_assets = h->N;
-    g.desc = B.bdesc[ph];
-    g.use_phaseA = ph == 0;
-    g.use_phaseB = ph == 1;
-    g.tile_store_out = 1;
-    g.out = h->store[ph];
-    StageTimer tm(h, BP_STAGE_GRAM);
-    CU_TRY(launch_gram(g, h->map_hf, h->map_d, h->sm_count, h->stream));
-    h->launches++;
+    for (int l = 0; l < 2; ++l) {
+        if (B.nblocks[ph][l] <= 0) continue;
+        GramParams g{};
+        g.n_windows = B.nblocks[ph][l];
+        g.n_assets = h->N;
+        g.desc = B.bdesc[ph][l];
+        g.use_phaseA = ph == 0;
+        g.use_phaseB = ph == 1;
+        g.tile_store_out = 1;
+        g.out = h->store[ph][l];
+        StageTimer tm(h, BP_STAGE_GRAM);
+        CU_TRY(launch_gram(g, h->map_hf, h->map_d, h->sm_count, h->stream));
+        h->launches++;
+    }
     return BP_OK;
 }
 
@@ -751,8 +824,8 @@ int bp_destroy(bp_handle* h) {
     cudaEventDestroy(h->ev_hf);
     cudaFree(h->desc);
     cudaFreeHost(h->desc_host);
-    cudaFree(h->store[0]);
-    cudaFree(h->store[1]);
+    for (int a = 0; a < 2; ++a)
+        for (int l = 0; l < 2; ++l) cudaFree(h->store[a][l]);
     cudaFree(h->prior_n);
     cudaFree(h->ws);
     cudaFree(h->stage);

@@ -16,7 +16,9 @@
 // row / one day of intraday bars), so the row range of a phase is split on a fixed block grid:
 //   * rows inside whole blocks are NOT contracted again: the block's 128x128 Gram tile was computed once
 //     (same kernel, tile_store_out mode) and is streamed from L2 into the accumulators ("ADD" items,
-//     64 KB halves by cp.async.bulk into the same stage ring);
+//     64 KB halves by cp.async.bulk into the same stage ring); two grid levels (coarse blocks in the
+//     middle of the window, fine blocks next to its ends) keep both the number of tiles added and the
+//     number of rows left for the tensor cores small;
 //   * only the partial head / tail rows of the window go through the tensor cores ("K" items).
 // All terms are still exact FP64 sums of the same products, only associated differently (no subtraction,
 // no running update), so the result differs from a from-scratch contraction by a few ulp.
@@ -46,16 +48,18 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                  : "memory");
 }
 
-// One job = (window, tile pair).  Its items, in order:
-//   group 0/1: K items of phase A segments 0/1     group 2: ADD items of phase A (2 per block)
-//   group 3/4: K items of phase B segments 0/1     group 5: ADD items of phase B
+// One job = (window, tile pair).  Its items, in order, per phase (A then B):
+//   K items of the head rows, K items of the tail rows, ADD items (2 per block) of the coarse blocks, of the
+//   fine blocks on the head side and of the fine blocks on the tail side
+constexpr int NGROUPS = 10;
 struct JobState {
     int job, w, ti, tj, pair;
-    int row0_0, row0_1, row0_2, row0_3;   // first row of K segment A0, A1, B0, B1
-    int rows_0, rows_1, rows_2, rows_3;   // row counts
-    int blk0_0, blk0_1;                   // first stored block of phase A / B
-    int end0, end1, end2, end3, end4, end5;   // cumulative item counts of the six groups
+    int base[NGROUPS];    // K groups: first row; ADD groups: first block
+    int rows[NGROUPS];    // K groups: row count (ADD groups: unused)
+    int end[NGROUPS];     // cumulative item counts
 };
+// group kinds per phase: 0,1 = K ; 2 = coarse ADD ; 3,4 = fine ADD
+__device__ __forceinline__ bool group_is_add(int g) { return (g % 5) >= 2; }
 
 __device__ __forceinline__ void job_setup(JobState& js, const GramParams& p, int job, int npairs) {
     js.job = job;
@@ -68,33 +72,40 @@ __device__ __forceinline__ void job_setup(JobState& js, const GramParams& p, int
     js.tj = pr - ti * (ti + 1) / 2;
     js.pair = pr;
     const int* d = p.desc + (long long)w * GRAM_DESC_INTS;
-    const bool onA = p.use_phaseA != 0, onB = p.use_phaseB != 0;
-    js.row0_0 = d[0]; js.rows_0 = onA ? d[1] : 0;
-    js.row0_1 = d[2]; js.rows_1 = onA ? d[3] : 0;
-    js.blk0_0 = d[4];
-    const int nblkA = onA ? d[5] : 0;
-    js.row0_2 = d[6]; js.rows_2 = onB ? d[7] : 0;
-    js.row0_3 = d[8]; js.rows_3 = onB ? d[9] : 0;
-    js.blk0_1 = d[10];
-    const int nblkB = onB ? d[11] : 0;
     int e = 0;
-    e += (js.rows_0 + GRAM_KT - 1) / GRAM_KT; js.end0 = e;
-    e += (js.rows_1 + GRAM_KT - 1) / GRAM_KT; js.end1 = e;
-    e += 2 * nblkA;                           js.end2 = e;
-    e += (js.rows_2 + GRAM_KT - 1) / GRAM_KT; js.end3 = e;
-    e += (js.rows_3 + GRAM_KT - 1) / GRAM_KT; js.end4 = e;
-    e += 2 * nblkB;                           js.end5 = e;
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+        const bool on = ph == 0 ? p.use_phaseA != 0 : p.use_phaseB != 0;
+        const int* dp = d + ph * GRAM_PHASE_INTS;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int g = ph * 5 + k;
+            const int cnt = on ? dp[2 * k + 1] : 0;
+            js.base[g] = dp[2 * k];
+            js.rows[g] = cnt;
+            e += k < 2 ? (cnt + GRAM_KT - 1) / GRAM_KT : 2 * cnt;
+            js.end[g] = e;
+        }
+    }
 }
 
-// decode flat item f of a job: group (0..5), index inside the group, and for K items the segment's
-// first row / row count
-__device__ __forceinline__ void item_decode(const JobState& js, int f, int& grp, int& idx, int& row0, int& rows) {
-    if (f < js.end0)      { grp = 0; idx = f;           row0 = js.row0_0; rows = js.rows_0; }
-    else if (f < js.end1) { grp = 1; idx = f - js.end0; row0 = js.row0_1; rows = js.rows_1; }
-    else if (f < js.end2) { grp = 2; idx = f - js.end1; row0 = js.blk0_0; rows = 0; }
-    else if (f < js.end3) { grp = 3; idx = f - js.end2; row0 = js.row0_2; rows = js.rows_2; }
-    else if (f < js.end4) { grp = 4; idx = f - js.end3; row0 = js.row0_3; rows = js.rows_3; }
-    else                  { grp = 5; idx = f - js.end4; row0 = js.blk0_1; rows = 0; }
+// decode flat item f of a job: group and index inside the group
+__device__ __forceinline__ void item_decode(const JobState& js, int f, int& grp, int& idx, int& base, int& rows) {
+    grp = 0;
+#pragma unroll
+    for (int k = 0; k < NGROUPS - 1; ++k)
+        if (f >= js.end[k]) grp = k + 1;
+    int prev = 0;
+    base = js.base[0];
+    rows = js.rows[0];
+#pragma unroll
+    for (int k = 1; k < NGROUPS; ++k)
+        if (grp == k) {
+            prev = js.end[k - 1];
+            base = js.base[k];
+            rows = js.rows[k];
+        }
+    idx = f - prev;
 }
 
 template <bool MASK>
@@ -147,6 +158,7 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                  const GramParams p) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t full_bar[GRAM_STAGES];
+    __shared__ uint64_t empty_bar[GRAM_STAGES];    // one arrival per consumer warp: no block barrier per item
     // 1024-byte alignment for the 128B swizzle, by pointer arithmetic on the shared array itself so that
     // the compiler keeps the shared address space (an integer round trip degrades every LDS to a generic LD)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -161,7 +173,10 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     if (tid == 0) {
         tma_prefetch_desc(&map0);
         tma_prefetch_desc(&map1);
-        for (int s = 0; s < GRAM_STAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < GRAM_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], GRAM_THREADS / 32);
+        }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -182,7 +197,7 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         int nj = first;                      // jobs without items are skipped by producer and consumer alike
         while (nj < njobs) {
             job_setup(pj, p, nj, npairs);
-            if (pj.end5 > 0) break;
+            if (pj.end[NGROUPS - 1] > 0) break;
             nj += gridDim.x;
         }
         pvalid = nj < njobs;
@@ -191,24 +206,26 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     auto producer_issue = [&]() {
         const int stage = pit % GRAM_STAGES;
         unsigned char* sA = smem + stage * STAGE_BYTES;
-        int grp, idx, row0, rows;
-        item_decode(pj, pf, grp, idx, row0, rows);
-        if (grp == 2 || grp == 5) {
-            const double* store = grp == 2 ? p.storeA : p.storeB;
-            const double* src = store + ((long long)(row0 + (idx >> 1)) * npairs + pj.pair) * GRAM_BLOCK_TILE_DOUBLES +
+        // the stage is free once every consumer warp has released its previous use
+        if (pit >= GRAM_STAGES) mbar_wait(&empty_bar[stage], ((pit / GRAM_STAGES) - 1) & 1);
+        int grp, idx, base, rows;
+        item_decode(pj, pf, grp, idx, base, rows);
+        if (group_is_add(grp)) {
+            const double* store = p.store[grp / 5][(grp % 5) == 2 ? 0 : 1];
+            const double* src = store + ((long long)(base + (idx >> 1)) * npairs + pj.pair) * GRAM_BLOCK_TILE_DOUBLES +
                                 (idx & 1) * (GRAM_BLOCK_TILE_DOUBLES / 2);
             mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
             bulk_load(sA, src, STAGE_BYTES, &full_bar[stage]);
         } else {
-            const int row = row0 + idx * GRAM_KT;
-            const void* map = grp < 2 ? static_cast<const void*>(&map0) : static_cast<const void*>(&map1);
+            const int row = base + idx * GRAM_KT;
+            const void* map = grp < 5 ? static_cast<const void*>(&map0) : static_cast<const void*>(&map1);
             const bool diag = pj.ti == pj.tj;
             mbar_arrive_expect_tx(&full_bar[stage], diag ? TILE_BYTES : STAGE_BYTES);
             tma_load_3d(sA, map, 0, row, pj.ti * 8, &full_bar[stage]);
             if (!diag) tma_load_3d(sA + TILE_BYTES, map, 0, row, pj.tj * 8, &full_bar[stage]);
         }
         ++pit;
-        if (++pf == pj.end5) producer_advance_job(pj.job + gridDim.x);
+        if (++pf == pj.end[NGROUPS - 1]) producer_advance_job(pj.job + gridDim.x);
     };
     if (tid == 0) {
         producer_advance_job(blockIdx.x);
@@ -226,15 +243,15 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
         const bool diag = js.ti == js.tj;
-        const int nitems = js.end5;
+        const int nitems = js.end[NGROUPS - 1];
         for (int f = 0; f < nitems; ++f, ++it) {
             const int stage = it % GRAM_STAGES;
             const uint32_t parity = (it / GRAM_STAGES) & 1;
-            int grp, idx, row0, rows;
-            item_decode(js, f, grp, idx, row0, rows);
+            int grp, idx, base, rows;
+            item_decode(js, f, grp, idx, base, rows);
             const unsigned char* sA = smem + stage * STAGE_BYTES;
             mbar_wait(&full_bar[stage], parity);
-            if (grp == 2 || grp == 5) {
+            if (group_is_add(grp)) {
                 if (idx & 1) add_half<1>(sA, acc, tid);
                 else add_half<0>(sA, acc, tid);
             } else {
@@ -245,9 +262,10 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 else
                     compute_tile<true>(sA, sB, kvalid, acc, offs0, offs1, cgA0, cgB0, tig);
             }
-            __syncthreads();                       // every warp is done with this stage
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);      // this warp is done with the stage
             if (tid == 0 && pvalid) producer_issue();
-            if (f == js.end2 - 1 && p.use_alpha) {        // last item of phase A: scale the HF Gram
+            if (f == js.end[4] - 1 && p.use_alpha) {      // last item of phase A: scale the HF Gram
                 const double alpha = p.scal[(long long)js.w * BP_S_COUNT + BP_S_ALPHA];
 #pragma unroll
                 for (int mt = 0; mt < 8; ++mt)

@@ -58,12 +58,14 @@ struct PrepParams {
     long long y_stride;
 };
 
-// Per-window job descriptor of the Gram kernel (GRAM_DESC_INTS ints):
-//   phase A (intraday, scaled by alpha):  [0] A0.row0 [1] A0.rows [2] A1.row0 [3] A1.rows [4] A.block0 [5] A.nblocks
-//   phase B (daily):                      [6] B0.row0 [7] B0.rows [8] B1.row0 [9] B1.rows [10] B.block0 [11] B.nblocks
-// K segments (row0, rows) go through the tensor cores; blocks [block0, block0+nblocks) of the phase's
-// tile store are added from memory.
-constexpr int GRAM_DESC_INTS = 12;
+// Per-window job descriptor of the Gram kernel (GRAM_DESC_INTS ints), 10 per phase (A = intraday, scaled by
+// alpha, at offset 0; B = daily at offset 10):
+//   [0] K0.row0 [1] K0.rows  [2] K1.row0 [3] K1.rows      head / tail rows contracted on the tensor cores
+//   [4] coarse.block0 [5] coarse.nblocks                   whole coarse blocks, added from the coarse tile store
+//   [6] fineA.block0  [7] fineA.nblocks                    whole fine blocks between the head rows and the coarse blocks
+//   [8] fineB.block0  [9] fineB.nblocks                    whole fine blocks between the coarse blocks and the tail rows
+constexpr int GRAM_DESC_INTS = 20;
+constexpr int GRAM_PHASE_INTS = 10;
 constexpr int GRAM_BLOCK_TILE_DOUBLES = 128 * 128;   // one stored 128x128 tile, fragment-major
 
 struct GramParams {
@@ -76,8 +78,9 @@ struct GramParams {
     const int* desc;         // [W][GRAM_DESC_INTS]
     int use_phaseA;          // contract / add the intraday phase (tensor map 0, storeA)
     int use_phaseB;          // contract / add the daily phase (tensor map 1, storeB)
-    const double* storeA;    // block tile stores: tile (block b, pair p) at ((b * npairs) + p) * GRAM_BLOCK_TILE_DOUBLES
-    const double* storeB;
+    // block tile stores [phase][level 0 = coarse, 1 = fine]: tile (block b, pair p) at
+    // ((b * npairs) + p) * GRAM_BLOCK_TILE_DOUBLES
+    const double* store[2][2];
     int tile_store_out;      // 1: block precompute, write raw accumulators fragment-major to out[(w*npairs+pair)*tile]
     const double* scal;      // [W][BP_S_COUNT] (alpha, beta)
     int use_alpha;
