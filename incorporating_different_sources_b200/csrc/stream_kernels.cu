@@ -126,7 +126,7 @@ __device__ __forceinline__ double2 reduce_cols(const double2 (&part)[NCH], doubl
     return s;
 }
 
-__global__ void __launch_bounds__(PREP_THREADS) window_prep_kernel(PrepParams p) {
+__global__ void __launch_bounds__(PREP_THREADS, 3) window_prep_kernel(PrepParams p) {
     extern __shared__ double smem[];
     const int K = p.n_window - 1;                 // daily returns per window (F2)
     double* a_s = smem;                           // [K]
