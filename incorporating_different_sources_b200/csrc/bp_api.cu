@@ -8,7 +8,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/bayes_portfolio.h"
@@ -83,6 +85,8 @@ struct bp_handle {
     // block tile stores of the Gram kernel (window-overlap reuse) and the smallest batch that uses them
     double* store[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [phase][level]
     size_t store_cap[2][2] = {{0, 0}, {0, 0}};                           // capacity in doubles
+    double* rstore[2] = {nullptr, nullptr};                              // phase-B range-sum stores [level]
+    size_t rstore_cap[2] = {0, 0};
     int reuse_min_windows = 32;
     // work counters of the Gram stage since the last bp_get_gram_work (bench.py's roofline accounting)
     double work_k_rows = 0, work_add_blocks = 0, work_pre_rows = 0, work_full_rows = 0;
@@ -258,6 +262,8 @@ struct Batch {
     const int* gdesc = nullptr;        // [W][GRAM_DESC_INTS] Gram job descriptors
     const int* bdesc[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // block precompute launches [phase][level]
     int nblocks[2][2] = {{0, 0}, {0, 0}};
+    const int* rdesc[2] = {nullptr, nullptr};      // phase B: [lo, hi) block ranges to pre-sum, per level
+    int nranges[2] = {0, 0};
 };
 
 // Block grids of one phase, two levels (0 = coarse, 1 = fine; the fine size divides the coarse size): block b of
@@ -386,6 +392,9 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         row0 = ph == 0 ? b->hf_lo[w] + 1 : b->day_row[w] - n + 2;
         rows = ph == 0 ? b->hf_hi[w] - b->hf_lo[w] - 1 : n - 1;
     };
+    // phase B (daily rows): the run of whole blocks inside a window is the same for many consecutive windows, so
+    // each distinct run [lo, hi) is summed once (range_sum_kernel) and a window adds one tile per run
+    std::map<std::pair<long long, long long>, int> range_id[2];
     // first pass: block ranges touched by the windows, per level
     for (int ph = 0; ph < 2; ++ph) {
         if (plan[ph].blk[0] <= 0 && plan[ph].blk[1] <= 0) continue;
@@ -398,6 +407,11 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             if (sp.c_hi > sp.c_lo) { lo[0] = std::min(lo[0], sp.c_lo); hi[0] = std::max(hi[0], sp.c_hi); }
             if (sp.fa_hi > sp.fa_lo) { lo[1] = std::min(lo[1], sp.fa_lo); hi[1] = std::max(hi[1], sp.fa_hi); }
             if (sp.fb_hi > sp.fb_lo) { lo[1] = std::min(lo[1], sp.fb_lo); hi[1] = std::max(hi[1], sp.fb_hi); }
+            if (ph == 1) {
+                if (sp.c_hi > sp.c_lo) range_id[0].emplace(std::make_pair(sp.c_lo, sp.c_hi), 0);
+                if (sp.fa_hi > sp.fa_lo) range_id[1].emplace(std::make_pair(sp.fa_lo, sp.fa_hi), 0);
+                if (sp.fb_hi > sp.fb_lo) range_id[1].emplace(std::make_pair(sp.fb_lo, sp.fb_hi), 0);
+            }
         }
         for (int l = 0; l < 2; ++l) {
             if (hi[l] <= lo[l]) { plan[ph].blk[l] = 0; plan[ph].nb[l] = 0; continue; }
@@ -418,8 +432,23 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             }
         }
     }
+    int nranges[2] = {0, 0};
+    for (int l = 0; l < 2; ++l) {
+        if (plan[1].blk[l] <= 0) { range_id[l].clear(); continue; }
+        for (auto& kv : range_id[l]) kv.second = nranges[l]++;
+        const size_t need = (size_t)nranges[l] * npairs_t * GRAM_BLOCK_TILE_DOUBLES;
+        if (need > h->rstore_cap[l]) {
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            cudaFree(h->rstore[l]);
+            h->rstore[l] = nullptr;
+            h->rstore_cap[l] = 0;
+            CU_TRY(cudaMalloc(&h->rstore[l], need * sizeof(double)));
+            h->rstore_cap[l] = need;
+        }
+    }
     const int nb_total = plan[0].nb[0] + plan[0].nb[1] + plan[1].nb[0] + plan[1].nb[1];
-    const size_t ints_needed = (size_t)(7 + GRAM_DESC_INTS) * W + (size_t)GRAM_DESC_INTS * nb_total;
+    const size_t ints_needed = (size_t)(7 + GRAM_DESC_INTS) * W + (size_t)GRAM_DESC_INTS * nb_total +
+                               2 * (size_t)(nranges[0] + nranges[1]);
     if (ints_needed > h->desc_cap) {
         if (h->desc) {
             CU_TRY(cudaStreamSynchronize(h->stream));
@@ -474,7 +503,13 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             dB[0] = dr - (n - 2) + 1; dB[1] = n - 2;       // shared weekly rows
             dB[2] = b->extra_row[w];  dB[3] = 1;           // the trade date's own row
         } else {
-            write_phase_desc(split_rows(dr - n + 2, n - 1, plan[1]), plan[1], gd + (size_t)w * GRAM_DESC_INTS + GRAM_PHASE_INTS);
+            const Split sp = split_rows(dr - n + 2, n - 1, plan[1]);
+            int* dB = gd + (size_t)w * GRAM_DESC_INTS + GRAM_PHASE_INTS;
+            write_phase_desc(sp, plan[1], dB);
+            // one pre-summed tile per run of whole blocks
+            if (dB[5] > 0) { dB[4] = range_id[0][std::make_pair(sp.c_lo, sp.c_hi)]; dB[5] = 1; }
+            if (dB[7] > 0) { dB[6] = range_id[1][std::make_pair(sp.fa_lo, sp.fa_hi)]; dB[7] = 1; }
+            if (dB[9] > 0) { dB[8] = range_id[1][std::make_pair(sp.fb_lo, sp.fb_hi)]; dB[9] = 1; }
         }
         const int* d = gd + (size_t)w * GRAM_DESC_INTS;
         auto r8 = [](int r) { return (r + 7) / 8 * 8; };
@@ -500,6 +535,16 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             out->nblocks[ph][l] = plan[ph].nb[l];
             bd += (size_t)plan[ph].nb[l] * GRAM_DESC_INTS;
         }
+    // block runs to pre-sum (store-relative block indices)
+    for (int l = 0; l < 2; ++l) {
+        for (const auto& kv : range_id[l]) {
+            bd[2 * kv.second] = (int)(kv.first.first - plan[1].bmin[l]);
+            bd[2 * kv.second + 1] = (int)(kv.first.second - plan[1].bmin[l]);
+        }
+        out->rdesc[l] = nranges[l] ? h->desc + (bd - host) : nullptr;
+        out->nranges[l] = nranges[l];
+        bd += 2 * (size_t)nranges[l];
+    }
     out->gdesc = h->desc + (size_t)7 * W;
     out->resampled = rs;
     out->extra_row = rs ? h->desc + 5 * (size_t)W : nullptr;
@@ -626,8 +671,10 @@ GramParams gram_params(const bp_handle* h, const Batch& B, const Layout& L, cons
     g.scal = c.scal;
     g.out = c.S;
     g.desc = B.gdesc + (size_t)w0 * GRAM_DESC_INTS;
-    for (int a = 0; a < 2; ++a)
-        for (int l = 0; l < 2; ++l) g.store[a][l] = h->store[a][l];
+    for (int l = 0; l < 2; ++l) {
+        g.store[0][l] = h->store[0][l];          // intraday: one tile per whole block
+        g.store[1][l] = h->rstore[l];            // daily: one pre-summed tile per run of whole blocks
+    }
     const bool hf = kind == GRAM_S0 || kind == GRAM_S1;
     const bool daily = kind != GRAM_S0;
     g.use_phaseA = hf;
@@ -660,6 +707,12 @@ int run_block_precompute(bp_handle* h, const Batch& B, int ph) {
         StageTimer tm(h, BP_STAGE_GRAM);
         CU_TRY(launch_gram(g, h->map_hf, h->map_d, h->sm_count, h->stream));
         h->launches++;
+        if (ph == 1 && B.nranges[l] > 0) {
+            const int nt = (h->N + GRAM_TILE - 1) / GRAM_TILE;
+            launch_range_sum(h->store[1][l], B.rdesc[l], B.nranges[l], nt * (nt + 1) / 2, h->rstore[l], h->stream);
+            h->launches++;
+            CU_TRY(cudaGetLastError());
+        }
     }
     return BP_OK;
 }
@@ -826,6 +879,8 @@ int bp_destroy(bp_handle* h) {
     cudaFreeHost(h->desc_host);
     for (int a = 0; a < 2; ++a)
         for (int l = 0; l < 2; ++l) cudaFree(h->store[a][l]);
+    cudaFree(h->rstore[0]);
+    cudaFree(h->rstore[1]);
     cudaFree(h->prior_n);
     cudaFree(h->ws);
     cudaFree(h->stage);

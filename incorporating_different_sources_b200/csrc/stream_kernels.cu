@@ -372,6 +372,35 @@ void launch_gather_log_returns(const double* P, int ld_in, const int* num, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// Range sums of stored block tiles (Gram reuse): out[r] = sum_{b in [lo_r, hi_r)} store[b], tile by tile.  The run
+// of whole blocks inside a window is the same for many consecutive windows (it changes only when a window edge
+// crosses a block boundary), so it is summed once here and each window adds ONE tile instead of hi-lo tiles.
+// Summation order: ascending block index (deterministic).  ranges = [lo_0, hi_0, lo_1, hi_1, ...].
+__global__ void range_sum_kernel(const double* __restrict__ store, const int* __restrict__ ranges, int npairs,
+                                 double* __restrict__ out) {
+    const int r = blockIdx.y;
+    const int lo = ranges[2 * r], hi = ranges[2 * r + 1];
+    const long long per_block = (long long)npairs * (GRAM_BLOCK_TILE_DOUBLES / 2);      // double2 elements per block
+    const double2* src = reinterpret_cast<const double2*>(store);
+    double2* dst = reinterpret_cast<double2*>(out) + (long long)r * per_block;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_block; i += (long long)gridDim.x * blockDim.x) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int b = lo; b < hi; ++b) {
+            const double2 v = src[(long long)b * per_block + i];
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+        dst[i] = acc;
+    }
+}
+
+void launch_range_sum(const double* store, const int* ranges, int n_ranges, int npairs, double* out, cudaStream_t st) {
+    if (n_ranges <= 0) return;
+    dim3 grid(64, n_ranges);
+    range_sum_kernel<<<grid, 256, 0, st>>>(store, ranges, npairs, out);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Window descriptors travel host -> device through a page-locked host buffer read by this kernel (zero-copy
 // over PCIe) instead of a cudaMemcpy: the host->device copy engine may be busy for tens of milliseconds with
 // the intraday block, and a queued 80 KB descriptor copy would stall every stage that does not even read it.
