@@ -14,10 +14,17 @@
 //                     (2-D tensor map over the whole workspace, 32-row x 16-column boxes,
 //                     SWIZZLE_128B, 3-stage mbarrier ring) in slabs of 8*TPW m-tiles; each warp owns TPW
 //                     8-row m-tiles of the slab and all four 8-column n-tiles of the panel.
-//   F  diagonal block 32x32 right-looking Cholesky + triangular inverse by the whole CTA in shared
-//                     memory (one short pivot chain + a 4-element rank-1 update per thread and step;
-//                     a single warp doing this alone is latency bound and took 2/3 of the kernel)
-//   T  panel solve    L[j0+32:, j0:j0+32] = C * inv(L_d)' on the tensor cores
+//   F  diagonal block 32x32 right-looking Cholesky AND its triangular inverse in ONE 32-step loop by the
+//                     whole CTA in shared memory (one barrier per step; a single warp doing this alone is
+//                     latency bound and took 2/3 of the kernel).  The diagonal block lives in the first
+//                     slab, so F runs right after that slab's update.
+//   T  panel solve    L[j0+32:, j0:j0+32] = C * inv(L_d)' on the tensor cores, FUSED into the epilogue of
+//                     the panel update: the accumulator fragment of a DMMA is, column for column, a valid
+//                     A fragment (lane (g,tig) holds columns 8nt+2tig+h, which become the k slots of step
+//                     (nt,h)), so C never goes to memory: the accumulators start as -S, collect +L L',
+//                     are multiplied by inv(L_d)' from registers, and the finished factor rows are stored
+//                     once.  (The first version wrote C and re-read it in a separate T phase: 2 MB of DRAM
+//                     traffic per window and 15% of the kernel.)
 // The factor is written with generic stores and re-read by TMA in later panels, so every panel ends
 // with fence.proxy.async + a block barrier.  The right-hand side rides along as one extra row
 // (row Nr = roundup(N,32)) of the matrix, so the forward substitution L z = b is a by-product of
@@ -37,7 +44,6 @@
 namespace bp {
 
 constexpr int NB = 32;
-constexpr int LDP = 33;    // padded shared-memory row stride of the 32x32 blocks
 
 #ifndef CH_NWARPS
 #define CH_NWARPS 4
@@ -49,56 +55,67 @@ constexpr int CH_WARPS = CH_NWARPS;                 // warps per window (CTA)
 constexpr int CH_OCC = CH_CTAS_PER_SM;              // resident CTAs (windows) per SM
 constexpr int CH_THREADS = CH_WARPS * 32;
 
-// 32x32 Cholesky + triangular inverse of the diagonal block in Ld (stride LDP) by the WHOLE CTA.
-// A single warp running this is pure latency (measured: 200k cycles per panel, 2/3 of the kernel, at
-// ~13 cycles per dependent instruction); with 256 threads every step is one short pivot chain
-// (load, rsqrt, multiply, store by warp 0) plus a rank-1 update in which each thread owns 4 elements.
-// Leaves L in Ld (upper part zeroed), 1/diag in invd and inv(L) in Li.  Returns (to every thread)
-// the 1-based index of the first non-positive pivot, or 0.
-__device__ __forceinline__ int potrf_trtri_block(double* Ld, double* Li, double* invd, int tid) {
+constexpr int LDQ = 34;    // row stride of the packed diagonal-block array
+
+// 32x32 Cholesky AND triangular inverse of the diagonal block by the WHOLE CTA, one barrier per step.
+// In : C (lower triangle) at P[r*LDQ + c], c <= r.
+// Out: L in the same place; inv(L) TRANSPOSED and shifted by one column in the strictly upper part,
+//      inv(L)[n][k] at P[k*LDQ + n + 1] (k <= n) -- the layout in which the B fragments of the fused panel
+//      solve are bank-conflict free (8-byte bank (4*tig + g + const) mod 16); 1/diag in invd.
+// Returns (to every thread) the 1-based index of the first non-positive pivot, or 0.
+//
+// Step k, Cholesky part (thread = row i, EPT consecutive columns): reads the UNSCALED column k and the
+// pivot, derives its own l_i and l_j (rsqrt recomputed by every thread instead of being broadcast through
+// a second barrier) and updates its trailing elements k < j <= i.  The scaled column k is written one step
+// later, after the barrier, when nobody reads column k any more.
+// Step k, inverse part (thread = inverse row iy = lane, EPT inverse columns of its warp): with
+// Y[i][j] = inv(L)[i][j] * L[i][i] (row scaling deferred to the end), Y[i][k] = -m_ik and
+// Y[i][j] -= m_ik Y[k][j] for j < k < i, m_ik = A[i][k] / pivot.  Reads column k+1, writes columns > k+1.
+__device__ __forceinline__ int potrf_trtri_block(double* P, double* invd, int tid) {
     constexpr int TPR = CH_THREADS / NB;   // threads per row of the block
     constexpr int EPT = NB / TPR;          // consecutive elements owned by a thread
-    const int i = tid / TPR;               // row owned by this thread
-    const int jb = (tid % TPR) * EPT;      // its EPT consecutive columns
+    static_assert(TPR == CH_WARPS, "inverse part: one warp per group of EPT inverse columns");
+    const int i = tid / TPR;               // Cholesky part: row owned by this thread
+    const int jb = (tid % TPR) * EPT;      //                its EPT consecutive columns
+    const int iy = tid & 31;               // inverse part: inverse row owned by this thread
+    const int jy = (tid >> 5) * EPT;       //               its EPT inverse columns (warp-uniform)
     int fail = 0;
-    // One barrier per step: every thread reads the UNSCALED column k and the pivot, derives its own
-    // l_i and l_j (the rsqrt is recomputed by all threads instead of being broadcast through another
-    // barrier) and updates its 4 trailing elements (columns > k: nobody reads those in this step).
-    // The scaled column k is written one step later, after the barrier, when nobody reads column k any more.
     double lprev = 0.0;
     for (int k = 0; k < NB; ++k) {
-        const double piv = Ld[k * LDP + k];
+        const double piv = P[k * LDQ + k];
         if (!(piv > 0.0) && fail == 0) fail = k + 1;
         const double inv = rsqrt(piv);
-        const double li = i > k ? Ld[i * LDP + k] * inv : (i == k ? piv * inv : 0.0);
-        if (k > 0 && k - 1 >= jb && k - 1 < jb + EPT) Ld[i * LDP + k - 1] = lprev;    // deferred scaled column k-1
+        const double li = i > k ? P[i * LDQ + k] * inv : (i == k ? piv * inv : 0.0);
+        const double my = iy > k ? P[iy * LDQ + k] * inv * inv : 0.0;
+        if (k > 0 && k - 1 >= jb && k - 1 < jb + EPT && i >= k - 1) P[i * LDQ + k - 1] = lprev;   // deferred column k-1
         if (k >= jb && k < jb + EPT) lprev = li;
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int j = jb + e;
-            if (j > k) Ld[i * LDP + j] = fma(-li, Ld[j * LDP + k] * inv, Ld[i * LDP + j]);
+            if (j > k && j <= i) P[i * LDQ + j] = fma(-li, P[j * LDQ + k] * inv, P[i * LDQ + j]);
+        }
+        if (iy > k) {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int j = jy + e;
+                if (j < k) P[j * LDQ + iy + 1] = fma(-my, P[j * LDQ + k + 1], P[j * LDQ + iy + 1]);
+                else if (j == k) P[j * LDQ + iy + 1] = -my;
+            }
         }
         if (tid == 0) invd[k] = inv;
         __syncthreads();
     }
-    if (NB - 1 >= jb && NB - 1 < jb + EPT) Ld[i * LDP + NB - 1] = lprev;
-    __syncthreads();
+    if (NB - 1 >= jb && NB - 1 < jb + EPT && i >= NB - 1) P[i * LDQ + NB - 1] = lprev;
+    // row scaling of the inverse: inv(L)[i][j] = Y[i][j] / L[i][i], inv(L)[i][i] = 1 / L[i][i]
+    {
+        const double d = invd[iy];
 #pragma unroll
-    for (int e = 0; e < EPT; ++e)
-        if (jb + e > i) Ld[i * LDP + jb + e] = 0.0;
-    // inverse X = inv(L): column j = tid & 31, the 8 warps split the rows of every update step
-    const int j = tid & 31, part = tid >> 5;
-    for (int r = part; r < NB; r += CH_WARPS) Li[r * LDP + j] = r == j ? 1.0 : 0.0;
-    __syncthreads();
-    double xprev = 0.0;
-    for (int q = 0; q < NB; ++q) {
-        const double xq = Li[q * LDP + j] * invd[q];          // row q is complete (barrier of step q-1)
-        if (part == 0 && q > 0) Li[(q - 1) * LDP + j] = xprev;  // finalise the previous row: nobody reads it now
-        xprev = xq;
-        for (int r = q + 1 + part; r < NB; r += CH_WARPS) Li[r * LDP + j] = fma(-Ld[r * LDP + q], xq, Li[r * LDP + j]);
-        __syncthreads();
+        for (int e = 0; e < EPT; ++e) {
+            const int j = jy + e;
+            if (j < iy) P[j * LDQ + iy + 1] *= d;
+            else if (j == iy) P[j * LDQ + iy + 1] = d;
+        }
     }
-    if (part == 0) Li[(NB - 1) * LDP + j] = xprev;
     __syncthreads();
     return fail;
 }
@@ -134,15 +151,12 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
     __shared__ int fail_s;
     // 1024-byte alignment by pointer arithmetic on the shared array (keeps the shared address space)
     unsigned char* stage_mem = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
-    double* Ld = reinterpret_cast<double*>(stage_mem + CH_STAGES * CH_STAGE_BYTES);   // [32][33]
-    double* Li = reinterpret_cast<double*>(stage_mem);   // [32][33] inverse of the diagonal block: aliases the TMA
-                                                         // stages, which are idle between the U phases
-    double* invd = Ld + NB * LDP;          // [32] reciprocal diagonal of the current block
-    double* colk = invd + NB;              // [32] scaled pivot column of the current step
-    double* red = colk + NB;               // [CH_WARPS][32]
+    double* P = reinterpret_cast<double*>(stage_mem + CH_STAGES * CH_STAGE_BYTES);   // [32][LDQ]: L_d (lower) + inv(L_d)' (upper)
+    double* invd = P + NB * LDQ;           // [32] reciprocal diagonal of the current block
+    double* red = invd + NB;               // [CH_WARPS][32]
     double* scratch = red + CH_WARPS * NB; // [40]
-    // solution vector of the back substitution: aliases the TMA stages too (after the last panel they are idle)
-    double* xs = reinterpret_cast<double*>(stage_mem) + NB * LDP;   // [Nr]
+    // solution vector of the back substitution: aliases the TMA stages (after the last panel they are idle)
+    double* xs = reinterpret_cast<double*>(stage_mem);   // [Nr]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tig = lane & 3;
@@ -189,16 +203,11 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
         for (int j0 = 0; j0 < N; j0 += NB) {
             const int mt_total = (Nr + 8 - j0) / 8;        // m-tiles covering rows j0 .. Nr+7
             const int nchunks = j0 / 16;
-            // ---------------- U: panel update, one 256-row slab (32 m-tiles) per pass
+            // ---------------- U (+F after the first slab) + fused T, one slab of SLAB_TILES m-tiles per pass
             for (int slab0 = 0; slab0 < mt_total; slab0 += SLAB_TILES) {
                 const int slab_tiles = min(SLAB_TILES, mt_total - slab0);
                 const int nboxes = (slab_tiles + 3) >> 2;
                 const int slab_row = j0 + 8 * slab0;
-                double acc[TPW][4][2];
-#pragma unroll
-                for (int i = 0; i < TPW; ++i)
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) acc[i][nt][0] = acc[i][nt][1] = 0.0;
                 int ni = 0;                  // m-tiles this warp really has in this slab (warp-uniform)
 #pragma unroll
                 for (int i = 0; i < TPW; ++i) ni += (warp + CH_WARPS * i) < slab_tiles ? 1 : 0;
@@ -215,6 +224,27 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
                 };
                 if (tid == 0)
                     for (int c = 0; c < CH_STAGES && c < nchunks; ++c) issue(c, it + c);
+
+                // accumulators start as -S (identity rows for the padding), collect +L L': acc = -C
+                double acc[TPW][4][2];
+#pragma unroll
+                for (int i = 0; i < TPW; ++i) {
+                    const int row = j0 + 8 * (slab0 + warp + CH_WARPS * i) + g;
+                    const bool real = i < ni && (row < N || row == Nr);
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        const int col = j0 + 8 * nt + 2 * tig;
+                        double2 sv = make_double2(0.0, 0.0);
+                        if (real && col < N) sv = *reinterpret_cast<const double2*>(S + (long long)row * ld + col);
+                        if (real) {
+                            acc[i][nt][0] = -sv.x;
+                            acc[i][nt][1] = col + 1 < N ? -sv.y : 0.0;
+                        } else {
+                            acc[i][nt][0] = row == col ? -1.0 : 0.0;
+                            acc[i][nt][1] = row == col + 1 ? -1.0 : 0.0;
+                        }
+                    }
+                }
 
                 for (int c = 0; c < nchunks; ++c, ++it) {
                     const int stage = it % CH_STAGES;
@@ -241,109 +271,85 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
                     if (lane == 0) mbar_arrive(&empty_bar[stage]);   // this warp is done with the stage
                     if (tid == 0 && c + CH_STAGES < nchunks) issue(c + CH_STAGES, it + CH_STAGES);
                 }
-                // C = S - acc, masked for padding; diagonal-block tiles go to shared memory
+
+                // padding: rows N..Nr-1 and columns >= N of the workspace hold no data; whatever the update
+                // accumulated there is replaced by the identity (rows) / zero (columns)
+                if (slab_row + 8 * slab_tiles > N || j0 + NB > N) {
 #pragma unroll
-                for (int i = 0; i < TPW; ++i) {
-                    const int q = slab0 + warp + CH_WARPS * i;     // m-tile index within the panel
-                    if (i >= ni) continue;
-                    const int row = j0 + 8 * q + g;
-                    const bool real = row < N || row == Nr;
-                    const bool in_diag = q < NB / 8;
+                    for (int i = 0; i < TPW; ++i) {
+                        const int row = j0 + 8 * (slab0 + warp + CH_WARPS * i) + g;
+                        const bool real = row < N || row == Nr;
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) {
-                        const int col = j0 + 8 * nt + 2 * tig;
-                        double c0, c1;
-                        if (real) {
-                            double2 sv = make_double2(0.0, 0.0);
-                            if (col < N) sv = *reinterpret_cast<const double2*>(S + (long long)row * ld + col);
-                            c0 = col < N ? sv.x - acc[i][nt][0] : 0.0;
-                            c1 = col + 1 < N ? sv.y - acc[i][nt][1] : 0.0;
-                        } else {
-                            c0 = row == col ? 1.0 : 0.0;
-                            c1 = row == col + 1 ? 1.0 : 0.0;
-                        }
-                        if (in_diag) {
-                            const int lr = 8 * q + g, lc = 8 * nt + 2 * tig;
-                            Ld[lr * LDP + lc] = c0;
-                            Ld[lr * LDP + lc + 1] = c1;
-                        } else if (real && col < N) {
-                            *reinterpret_cast<double2*>(S + (long long)row * ld + col) = make_double2(c0, c1);
+                        for (int nt = 0; nt < 4; ++nt) {
+                            const int col = j0 + 8 * nt + 2 * tig;
+                            if (!real) {
+                                acc[i][nt][0] = row == col ? -1.0 : 0.0;
+                                acc[i][nt][1] = row == col + 1 ? -1.0 : 0.0;
+                            } else {
+                                if (col >= N) acc[i][nt][0] = 0.0;
+                                if (col + 1 >= N) acc[i][nt][1] = 0.0;
+                            }
                         }
                     }
                 }
-            }
-            __syncthreads();
-            PROF(0)
-            // ---------------- F: diagonal block
-            {
-                const int f = potrf_trtri_block(Ld, Li, invd, tid);
-                if (tid == 0 && f != 0 && fail_s == 0) fail_s = j0 + f;
-            }
-            PROF(1)
-            // write L_d back (lower part, real rows only)
-            for (int i = warp; i < NB; i += CH_WARPS) {
-                const int row = j0 + i, col = j0 + lane;
-                if (row < N && col < N && lane <= i) S[(long long)row * ld + col] = Ld[i * LDP + lane];
-            }
-            // ---------------- T: rows below the diagonal block (and the right-hand-side row):
-            // X = C * inv(L_d)' on the tensor cores; C tiles are re-read from global as A fragments with
-            // the same k-permutation as the panel update, B[k][n] = inv(L_d)[n][k] comes from shared memory
-            {
-                // the C tile of one m-tile as A fragments: local columns cA, cA+1, cA+8, cA+9 of both 16-wide halves
-                auto load_tile = [&](int q, double (&a)[8]) {
-                    const int row = j0 + 8 * q + g;
-                    const bool real = q < mt_total && (row < N || row == Nr);
+
+                if (slab0 == 0) {
+                    // ---------------- F: the diagonal block (m-tiles 0..3 of the first slab) goes to shared memory
 #pragma unroll
-                    for (int kc = 0; kc < 2; ++kc) {
-                        const int cA = 16 * kc + 2 * tig;
-                        double2 lo = make_double2(0.0, 0.0), hi = make_double2(0.0, 0.0);
-                        if (real) {
-                            const double* src = S + (long long)row * ld + j0 + cA;
-                            if (j0 + cA < N) lo = *reinterpret_cast<const double2*>(src);
-                            if (j0 + cA + 8 < N) hi = *reinterpret_cast<const double2*>(src + 8);
-                        }
-                        a[4 * kc + 0] = lo.x;
-                        a[4 * kc + 1] = j0 + cA + 1 < N ? lo.y : 0.0;
-                        a[4 * kc + 2] = hi.x;
-                        a[4 * kc + 3] = j0 + cA + 9 < N ? hi.y : 0.0;
-                    }
-                };
-                double a_cur[8], a_nxt[8];
-                int q = NB / 8 + warp;
-                load_tile(q, a_cur);
-                for (; q < mt_total; q += CH_WARPS) {
-                    load_tile(q + CH_WARPS, a_nxt);          // next tile's loads fly during this tile's DMMAs
-                    const int row = j0 + 8 * q + g;
-                    const bool real = row < N || row == Nr;
-                    double acc[4][2];
+                    for (int i = 0; i < TPW; ++i) {
+                        const int q = warp + CH_WARPS * i;
+                        if (i < ni && q < NB / 8) {
+                            const int lr = 8 * q + g;
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
-#pragma unroll
-                    for (int kc = 0; kc < 2; ++kc) {
-                        const int cA = 16 * kc + 2 * tig;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int k = cA + (e & 1) + 8 * (e >> 1);
-                            // this step contracts the 8-wide k block kb; inv(L_d)[n][k] = 0 for k > n, so
-                            // n-tiles left of the k block contribute nothing
-                            const int kb = 2 * kc + (e >> 1);
-#pragma unroll
-                            for (int nt = 0; nt < 4; ++nt)
-                                if (nt >= kb)
-                                    dmma884(acc[nt][0], acc[nt][1], a_cur[4 * kc + e], Li[(8 * nt + g) * LDP + k]);
+                            for (int nt = 0; nt < 4; ++nt) {
+                                const int lc = 8 * nt + 2 * tig;
+                                if (lc <= lr) P[lr * LDQ + lc] = -acc[i][nt][0];
+                                if (lc + 1 <= lr) P[lr * LDQ + lc + 1] = -acc[i][nt][1];
+                            }
                         }
                     }
-                    __syncwarp();    // every lane holds its part of the tile in registers before it is overwritten
-                    if (real) {
+                    __syncthreads();
+                    PROF(0)
+                    const int f = potrf_trtri_block(P, invd, tid);
+                    if (tid == 0 && f != 0 && fail_s == 0) fail_s = j0 + f;
+                    PROF(1)
+                    // write L_d back (lower part, real rows only)
+                    for (int i = warp; i < NB; i += CH_WARPS) {
+                        const int row = j0 + i, col = j0 + lane;
+                        if (row < N && col < N && lane <= i) S[(long long)row * ld + col] = P[i * LDQ + lane];
+                    }
+                }
+                // ---------------- T: X = C inv(L_d)' straight from the accumulators.  DMMA step (kt,h) contracts
+                // the columns 8kt+2tig+h the lanes already hold; B[k][n] = inv(L_d)[n][k] = P[k*LDQ + n + 1];
+                // inv(L_d)[n][k] = 0 for k > n, so n-tiles left of the k block are skipped
+#pragma unroll
+                for (int i = 0; i < TPW; ++i) {
+                    const int q = slab0 + warp + CH_WARPS * i;     // m-tile index within the panel
+                    if (i >= ni || q < NB / 8) continue;
+                    const int row = j0 + 8 * q + g;
+                    double y[4][2];
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) y[nt][0] = y[nt][1] = 0.0;
+#pragma unroll
+                    for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int k = 8 * kt + 2 * tig + h;
+#pragma unroll
+                            for (int nt = kt; nt < 4; ++nt) {
+                                double bv = P[k * LDQ + 8 * nt + g + 1];
+                                if (nt == kt && 2 * tig + h > g) bv = 0.0;
+                                dmma884(y[nt][0], y[nt][1], acc[i][kt][h], bv);
+                            }
+                        }
+                    if (row < N || row == Nr) {
 #pragma unroll
                         for (int nt = 0; nt < 4; ++nt) {
                             const int col = j0 + 8 * nt + 2 * tig;
                             if (col < N)
-                                *reinterpret_cast<double2*>(S + (long long)row * ld + col) = make_double2(acc[nt][0], acc[nt][1]);
+                                *reinterpret_cast<double2*>(S + (long long)row * ld + col) = make_double2(-y[nt][0], -y[nt][1]);
                         }
                     }
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) a_cur[e] = a_nxt[e];
                 }
             }
             fence_proxy_async_all();        // the factor written above is read by TMA in the next panels
@@ -382,19 +388,19 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
                 double v;
                 if (row < N && col < N) v = lane <= i ? S[(long long)row * ld + col] : 0.0;
                 else v = i == lane ? 1.0 : 0.0;
-                Ld[i * LDP + lane] = v;
+                P[i * LDQ + lane] = v;
             }
             __syncthreads();
             if (warp == 0) {
                 double r = xs[col];
 #pragma unroll
                 for (int wv = 0; wv < CH_WARPS; ++wv) r -= red[wv * NB + lane];
-                const double rd = 1.0 / Ld[lane * LDP + lane];      // all 32 reciprocals in parallel
+                const double rd = 1.0 / P[lane * LDQ + lane];      // all 32 reciprocals in parallel
 #pragma unroll
                 for (int k = NB - 1; k >= 0; --k) {
                     const double xk = __shfl_sync(0xffffffffu, r * rd, k);
                     if (lane == k) r = xk;
-                    if (lane < k) r = fma(-Ld[k * LDP + lane], xk, r);
+                    if (lane < k) r = fma(-P[k * LDQ + lane], xk, r);
                 }
                 xs[col] = r;
             }
@@ -430,9 +436,9 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
 
 size_t chol_smem_bytes(int n_assets) {
     const int Nr = (n_assets + NB - 1) / NB * NB;
-    // Li and xs alias the stage ring: it must hold them
-    if ((size_t)CH_STAGES * CH_STAGE_BYTES < sizeof(double) * (size_t)(NB * LDP + Nr)) return 0;
-    return (size_t)CH_TMA_SMEM + sizeof(double) * (size_t)(NB * LDP + 2 * NB + CH_WARPS * NB + 40);
+    // xs aliases the stage ring: it must hold it
+    if ((size_t)CH_STAGES * CH_STAGE_BYTES < sizeof(double) * (size_t)Nr) return 0;
+    return (size_t)CH_TMA_SMEM + sizeof(double) * (size_t)(NB * LDQ + NB + CH_WARPS * NB + 40);
 }
 
 cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int sm_count, cudaStream_t st) {
@@ -460,7 +466,7 @@ cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int
         cudaMemcpyAsync(hostv, dbg, sizeof(hostv), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         const double tot = (double)(hostv[0] + hostv[1] + hostv[2] + hostv[3] + hostv[4]);
-        fprintf(stderr, "[chol profile] W=%d U=%.1f%% F=%.1f%% T=%.1f%% backsub=%.1f%% out=%.1f%% cycles/window=%.0f\n", p.n_windows,
+        fprintf(stderr, "[chol profile] W=%d U(slab0)=%.1f%% F=%.1f%% U+T(rest)=%.1f%% backsub=%.1f%% out=%.1f%% cycles/window=%.0f\n", p.n_windows,
                 100 * hostv[0] / tot, 100 * hostv[1] / tot, 100 * hostv[2] / tot, 100 * hostv[3] / tot, 100 * hostv[4] / tot,
                 tot / p.n_windows);
         return cudaGetLastError();
