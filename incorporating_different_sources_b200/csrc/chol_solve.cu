@@ -57,67 +57,57 @@ constexpr int CH_THREADS = CH_WARPS * 32;
 
 constexpr int LDQ = 34;    // row stride of the packed diagonal-block array
 
-// 32x32 Cholesky AND triangular inverse of the diagonal block by the WHOLE CTA, one barrier per step.
-// In : C (lower triangle) at P[r*LDQ + c], c <= r.
-// Out: L in the same place; inv(L) TRANSPOSED and shifted by one column in the strictly upper part,
-//      inv(L)[n][k] at P[k*LDQ + n + 1] (k <= n) -- the layout in which the B fragments of the fused panel
-//      solve are bank-conflict free (8-byte bank (4*tig + g + const) mod 16); 1/diag in invd.
-// Returns (to every thread) the 1-based index of the first non-positive pivot, or 0.
-//
-// Step k, Cholesky part (thread = row i, EPT consecutive columns): reads the UNSCALED column k and the
-// pivot, derives its own l_i and l_j (rsqrt recomputed by every thread instead of being broadcast through
-// a second barrier) and updates its trailing elements k < j <= i.  The scaled column k is written one step
-// later, after the barrier, when nobody reads column k any more.
-// Step k, inverse part (thread = inverse row iy = lane, EPT inverse columns of its warp): with
-// Y[i][j] = inv(L)[i][j] * L[i][i] (row scaling deferred to the end), Y[i][k] = -m_ik and
-// Y[i][j] -= m_ik Y[k][j] for j < k < i, m_ik = A[i][k] / pivot.  Reads column k+1, writes columns > k+1.
-__device__ __forceinline__ int potrf_trtri_block(double* P, double* invd, int tid) {
-    constexpr int TPR = CH_THREADS / NB;   // threads per row of the block
-    constexpr int EPT = NB / TPR;          // consecutive elements owned by a thread
-    static_assert(TPR == CH_WARPS, "inverse part: one warp per group of EPT inverse columns");
-    const int i = tid / TPR;               // Cholesky part: row owned by this thread
-    const int jb = (tid % TPR) * EPT;      //                its EPT consecutive columns
-    const int iy = tid & 31;               // inverse part: inverse row owned by this thread
-    const int jy = (tid >> 5) * EPT;       //               its EPT inverse columns (warp-uniform)
+// Cholesky factor AND inverse of one 8x8 diagonal tile, by one warp, entirely in registers.
+// The tile is in DMMA accumulator layout: lane (g,tig) holds D[g][2tig], D[g][2tig+1] (lower part valid).
+// On return d0/d1 hold L (zero above the diagonal) and y0/y1 inv(L), same layout.  Eight steps, each one
+// round of shuffles (pivot, own-row and own-column entries of column k, row k of the inverse) and a
+// handful of FMAs -- the 32-step shared-memory loop this replaces cost 170 instructions per warp and step
+// and was a third of the kernel.  Inverse: with Y[i][j] = inv(L)[i][j] L[i][i], Y[i][j] -= (D[i][k]/piv) Y[k][j]
+// for j <= k < i; the row scaling is applied at the end.  Returns the 1-based index of the first
+// non-positive pivot, or 0.
+__device__ __forceinline__ int potrf8_inv8(double& d0, double& d1, double& y0, double& y1, int g, int tig, int lane) {
+    constexpr unsigned FULL = 0xffffffffu;
     int fail = 0;
-    double lprev = 0.0;
-    for (int k = 0; k < NB; ++k) {
-        const double piv = P[k * LDQ + k];
+    double u0 = 2 * tig == g ? 1.0 : 0.0, u1 = 2 * tig + 1 == g ? 1.0 : 0.0;
+    double invrow = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double dk = (k & 1) ? d1 : d0;
+        const int sq = k >> 1;
+        const double piv = __shfl_sync(FULL, dk, 4 * k + sq);               // D[k][k]
+        const double colg = __shfl_sync(FULL, dk, (lane & ~3) | sq);        // D[g][k]
+        const double colj0 = __shfl_sync(FULL, dk, 8 * tig + sq);           // D[2tig][k]
+        const double colj1 = __shfl_sync(FULL, dk, 8 * tig + 4 + sq);       // D[2tig+1][k]
+        const double yk0 = __shfl_sync(FULL, u0, 4 * k + tig);              // Y[k][2tig]
+        const double yk1 = __shfl_sync(FULL, u1, 4 * k + tig);              // Y[k][2tig+1]
         if (!(piv > 0.0) && fail == 0) fail = k + 1;
         const double inv = rsqrt(piv);
-        const double li = i > k ? P[i * LDQ + k] * inv : (i == k ? piv * inv : 0.0);
-        const double my = iy > k ? P[iy * LDQ + k] * inv * inv : 0.0;
-        if (k > 0 && k - 1 >= jb && k - 1 < jb + EPT && i >= k - 1) P[i * LDQ + k - 1] = lprev;   // deferred column k-1
-        if (k >= jb && k < jb + EPT) lprev = li;
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-            const int j = jb + e;
-            if (j > k && j <= i) P[i * LDQ + j] = fma(-li, P[j * LDQ + k] * inv, P[i * LDQ + j]);
+        const double lg = colg * inv;
+        const double mg = lg * inv;
+        if (g == k) invrow = inv;
+        if (g > k) {
+            if (2 * tig > k) d0 = fma(-lg, colj0 * inv, d0);
+            if (2 * tig + 1 > k) d1 = fma(-lg, colj1 * inv, d1);
+            if (2 * tig <= k) u0 = fma(-mg, yk0, u0);
+            if (2 * tig + 1 <= k) u1 = fma(-mg, yk1, u1);
         }
-        if (iy > k) {
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) {
-                const int j = jy + e;
-                if (j < k) P[j * LDQ + iy + 1] = fma(-my, P[j * LDQ + k + 1], P[j * LDQ + iy + 1]);
-                else if (j == k) P[j * LDQ + iy + 1] = -my;
-            }
-        }
-        if (tid == 0) invd[k] = inv;
-        __syncthreads();
-    }
-    if (NB - 1 >= jb && NB - 1 < jb + EPT && i >= NB - 1) P[i * LDQ + NB - 1] = lprev;
-    // row scaling of the inverse: inv(L)[i][j] = Y[i][j] / L[i][i], inv(L)[i][i] = 1 / L[i][i]
-    {
-        const double d = invd[iy];
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-            const int j = jy + e;
-            if (j < iy) P[j * LDQ + iy + 1] *= d;
-            else if (j == iy) P[j * LDQ + iy + 1] = d;
+        if (sq == tig) {
+            if (k & 1) d1 = g >= k ? lg : 0.0;
+            else d0 = g >= k ? lg : 0.0;
         }
     }
-    __syncthreads();
+    y0 = u0 * invrow;
+    y1 = u1 * invrow;
     return fail;
+}
+
+// B fragment of the panel solve: with W = L_d whose 8x8 diagonal tiles are replaced by their inverses,
+// W[8nb+n][8kb+k] sits TRANSPOSED and shifted by one column in the strictly upper part of P, at
+// P[(8kb+k)*LDQ + 8nb+n+1]; lanes (g,tig) read 8-byte bank (4 tig + g + const) mod 16: conflict free.
+// Inside a diagonal tile the entries above the diagonal (k > n) are zero (that spot holds L itself).
+__device__ __forceinline__ double wfrag(const double* P, int kb, int nb, int h, int g, int tig) {
+    const double v = P[(8 * kb + 2 * tig + h) * LDQ + 8 * nb + g + 1];
+    return (nb == kb && 2 * tig + h > g) ? 0.0 : v;
 }
 
 #ifndef CH_TPW
@@ -152,8 +142,7 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
     // 1024-byte alignment by pointer arithmetic on the shared array (keeps the shared address space)
     unsigned char* stage_mem = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
     double* P = reinterpret_cast<double*>(stage_mem + CH_STAGES * CH_STAGE_BYTES);   // [32][LDQ]: L_d (lower) + inv(L_d)' (upper)
-    double* invd = P + NB * LDQ;           // [32] reciprocal diagonal of the current block
-    double* red = invd + NB;               // [CH_WARPS][32]
+    double* red = P + NB * LDQ;            // [CH_WARPS][32]
     double* scratch = red + CH_WARPS * NB; // [40]
     // solution vector of the back substitution: aliases the TMA stages (after the last panel they are idle)
     double* xs = reinterpret_cast<double*>(stage_mem);   // [Nr]
@@ -294,24 +283,50 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
                 }
 
                 if (slab0 == 0) {
-                    // ---------------- F: the diagonal block (m-tiles 0..3 of the first slab) goes to shared memory
+                    // ---------------- F: 32x32 diagonal block, blocked by 8 in fragment space.  Warp q < 4 holds
+                    // row block q (acc[0][0..3] = -C).  Column block cb: warp cb factors and inverts its 8x8
+                    // tile in registers; the warps below solve their tile against it (2 DMMAs) and update their
+                    // remaining tiles (2 DMMAs each); L goes to the lower part of P, W' to the upper part.
+                    PROF(0)
 #pragma unroll
-                    for (int i = 0; i < TPW; ++i) {
-                        const int q = warp + CH_WARPS * i;
-                        if (i < ni && q < NB / 8) {
-                            const int lr = 8 * q + g;
+                    for (int cb = 0; cb < NB / 8; ++cb) {
+                        if (warp == cb) {
+                            double d0 = -acc[0][cb][0], d1 = -acc[0][cb][1], y0, y1;
+                            const int f = potrf8_inv8(d0, d1, y0, y1, g, tig, lane);
+                            if (lane == 0 && f != 0 && fail_s == 0) fail_s = j0 + 8 * cb + f;
+                            double* row = P + (8 * cb + g) * LDQ + 8 * cb + 2 * tig;
+                            if (2 * tig <= g) row[0] = d0;
+                            if (2 * tig + 1 <= g) row[1] = d1;
+                            if (2 * tig <= g) P[(8 * cb + 2 * tig) * LDQ + 8 * cb + g + 1] = y0;
+                            if (2 * tig + 1 <= g) P[(8 * cb + 2 * tig + 1) * LDQ + 8 * cb + g + 1] = y1;
+                        }
+                        __syncthreads();
+                        if (cb == NB / 8 - 1) break;
+                        if (warp > cb && warp < NB / 8) {
+                            double x0 = 0.0, x1 = 0.0;
 #pragma unroll
-                            for (int nt = 0; nt < 4; ++nt) {
-                                const int lc = 8 * nt + 2 * tig;
-                                if (lc <= lr) P[lr * LDQ + lc] = -acc[i][nt][0];
-                                if (lc + 1 <= lr) P[lr * LDQ + lc + 1] = -acc[i][nt][1];
-                            }
+                            for (int h = 0; h < 2; ++h) dmma884(x0, x1, acc[0][cb][h], wfrag(P, cb, cb, h, g, tig));
+                            x0 = -x0;
+                            x1 = -x1;
+                            acc[0][cb][0] = x0;      // this tile now holds +L
+                            acc[0][cb][1] = x1;
+                            double* row = P + (8 * warp + g) * LDQ + 8 * cb + 2 * tig;
+                            row[0] = x0;
+                            row[1] = x1;
+                            P[(8 * cb + 2 * tig) * LDQ + 8 * warp + g + 1] = x0;
+                            P[(8 * cb + 2 * tig + 1) * LDQ + 8 * warp + g + 1] = x1;
+                        }
+                        __syncthreads();
+                        if (warp > cb && warp < NB / 8) {
+#pragma unroll
+                            for (int nb = cb + 1; nb < NB / 8; ++nb)
+                                if (nb <= warp) {
+#pragma unroll
+                                    for (int h = 0; h < 2; ++h)
+                                        dmma884(acc[0][nb][0], acc[0][nb][1], acc[0][cb][h], wfrag(P, cb, nb, h, g, tig));
+                                }
                         }
                     }
-                    __syncthreads();
-                    PROF(0)
-                    const int f = potrf_trtri_block(P, invd, tid);
-                    if (tid == 0 && f != 0 && fail_s == 0) fail_s = j0 + f;
                     PROF(1)
                     // write L_d back (lower part, real rows only)
                     for (int i = warp; i < NB; i += CH_WARPS) {
@@ -319,35 +334,28 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
                         if (row < N && col < N && lane <= i) S[(long long)row * ld + col] = P[i * LDQ + lane];
                     }
                 }
-                // ---------------- T: X = C inv(L_d)' straight from the accumulators.  DMMA step (kt,h) contracts
-                // the columns 8kt+2tig+h the lanes already hold; B[k][n] = inv(L_d)[n][k] = P[k*LDQ + n + 1];
-                // inv(L_d)[n][k] = 0 for k > n, so n-tiles left of the k block are skipped
+                // ---------------- T: X = C inv(L_d)' straight from the accumulators, by block forward substitution
+                // with W: X_cb = C_cb inv(L_cb,cb)', C_nb -= X_cb L_nb,cb' (nb > cb).  DMMA step h contracts the
+                // columns 8cb+2tig+h the lanes already hold, so the accumulators are used as A fragments as they are.
 #pragma unroll
                 for (int i = 0; i < TPW; ++i) {
                     const int q = slab0 + warp + CH_WARPS * i;     // m-tile index within the panel
                     if (i >= ni || q < NB / 8) continue;
                     const int row = j0 + 8 * q + g;
-                    double y[4][2];
+                    const bool real = row < N || row == Nr;
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) y[nt][0] = y[nt][1] = 0.0;
+                    for (int cb = 0; cb < NB / 8; ++cb) {
+                        double x0 = 0.0, x1 = 0.0;
 #pragma unroll
-                    for (int kt = 0; kt < 4; ++kt)
+                        for (int h = 0; h < 2; ++h) dmma884(x0, x1, acc[i][cb][h], wfrag(P, cb, cb, h, g, tig));
+                        x0 = -x0;
+                        x1 = -x1;
+                        const int col = j0 + 8 * cb + 2 * tig;
+                        if (real && col < N) *reinterpret_cast<double2*>(S + (long long)row * ld + col) = make_double2(x0, x1);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int k = 8 * kt + 2 * tig + h;
-#pragma unroll
-                            for (int nt = kt; nt < 4; ++nt) {
-                                double bv = P[k * LDQ + 8 * nt + g + 1];
-                                if (nt == kt && 2 * tig + h > g) bv = 0.0;
-                                dmma884(y[nt][0], y[nt][1], acc[i][kt][h], bv);
-                            }
-                        }
-                    if (row < N || row == Nr) {
-#pragma unroll
-                        for (int nt = 0; nt < 4; ++nt) {
-                            const int col = j0 + 8 * nt + 2 * tig;
-                            if (col < N)
-                                *reinterpret_cast<double2*>(S + (long long)row * ld + col) = make_double2(-y[nt][0], -y[nt][1]);
+                        for (int nb = cb + 1; nb < NB / 8; ++nb) {
+                            dmma884(acc[i][nb][0], acc[i][nb][1], x0, wfrag(P, cb, nb, 0, g, tig));
+                            dmma884(acc[i][nb][0], acc[i][nb][1], x1, wfrag(P, cb, nb, 1, g, tig));
                         }
                     }
                 }
@@ -438,7 +446,7 @@ size_t chol_smem_bytes(int n_assets) {
     const int Nr = (n_assets + NB - 1) / NB * NB;
     // xs aliases the stage ring: it must hold it
     if ((size_t)CH_STAGES * CH_STAGE_BYTES < sizeof(double) * (size_t)Nr) return 0;
-    return (size_t)CH_TMA_SMEM + sizeof(double) * (size_t)(NB * LDQ + NB + CH_WARPS * NB + 40);
+    return (size_t)CH_TMA_SMEM + sizeof(double) * (size_t)(NB * LDQ + CH_WARPS * NB + 40);
 }
 
 cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int sm_count, cudaStream_t st) {
