@@ -148,6 +148,12 @@ int bp_get_gram_work(bp_handle* h, double* out4);
 /* Smallest batch (windows) for which the Gram kernel reuses precomputed block tiles between overlapping
  * windows; INT_MAX disables the reuse (every window is contracted from scratch). Default 32. */
 int bp_set_reuse_min_windows(bp_handle* h, int min_windows);
+/* Pipelining of bp_upload_market_async against bp_conjugate_batched: an intraday block of at least min_bytes
+ * is copied in `segments` pieces (1..8; 1 disables), each followed by its log returns, and the conjugate
+ * statistics / Gram stages of the windows whose bars have arrived run while the rest is still on the bus
+ * (the per-date loop of the reference, main.py:74 -> portfolio_calculations.py:1127, has no such ordering
+ * constraint: every date only reads bars up to that date).  Default: 8 segments from 256 MiB. */
+int bp_set_upload_pipeline(bp_handle* h, int segments, long long min_bytes);
 
 /* Host -> HBM: replaces the pandas frames of get_market_data() (data_handling.py:270-291).  Also
  * computes both log-return matrices on the device (:37, :314). */

@@ -77,6 +77,15 @@ struct bp_handle {
     cudaStream_t copy_stream = nullptr;                  // intraday H2D + its log-return kernel
     cudaEvent_t ev_main = nullptr, ev_hf = nullptr;
     bool hf_pending = false;
+    // an asynchronous intraday upload is cut into segments (copy + log returns + event each) so that the
+    // conjugate stages of the early rebalance dates run while the later bars are still on the bus
+    static constexpr int MAX_SEG = 8;
+    int pipe_segments = MAX_SEG;
+    size_t pipe_min_bytes = (size_t)256 << 20;
+    int n_seg = 0, seg_waited = 0;
+    long long lr_hf_done = 0;                  // intraday return rows < lr_hf_done have been computed
+    long long seg_end[MAX_SEG] = {0};          // return rows < seg_end[s] are valid once ev_seg[s] has fired
+    cudaEvent_t ev_seg[MAX_SEG] = {nullptr};
     CUtensorMap map_d, map_hf;
     // window descriptors on the device: day_row, span, row0, hf_row0, hf_m
     int* desc = nullptr;
@@ -149,11 +158,18 @@ void free_market(bp_handle* h) {
     h->has_market = false;
 }
 
-// conjugate stages read lr_hf, produced on the copy stream: order the compute stream after it
+// Conjugate stages read lr_hf.  The intraday prices arrive on the copy stream; their log returns are computed
+// on the COMPUTE stream once the copy event has fired (a kernel on the copy stream would have to wait for
+// free SMs behind the persistent Gram / solve kernels, and the next segment's copy would queue behind it).
 int wait_hf(bp_handle* h) {
     if (h->hf_pending) {
         CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_hf, 0));
+        launch_log_returns(h->hf_prices, h->N, h->lr_hf, h->ld, h->R, h->N, h->sm_count, h->stream, h->lr_hf_done);
+        h->launches++;
+        CU_TRY(cudaGetLastError());
+        h->lr_hf_done = h->R;
         h->hf_pending = false;
+        h->seg_waited = h->n_seg;
     }
     return BP_OK;
 }
@@ -250,6 +266,19 @@ Chunk carve(unsigned char* ws, const Layout& L, int Wc) {
     return c;
 }
 
+// the carved arrays as seen from window k of the chunk
+Chunk chunk_at(const Chunk& c, const Layout& L, int k) {
+    Chunk o = c;
+    o.S += (size_t)k * L.win_stride;
+    o.t += (size_t)k * L.ldv;       o.pvec += (size_t)k * L.ldv;  o.gvec += (size_t)k * L.ldv;
+    o.rhs += (size_t)k * L.ldv;     o.w0 += (size_t)k * L.ldv;    o.s0w0 += (size_t)k * L.ldv;
+    o.w1 += (size_t)k * L.ldv;      o.nu += (size_t)k * L.ldv;    o.weights += (size_t)k * L.ldv;
+    o.scal += (size_t)k * BP_NSCAL;
+    o.y += (size_t)k * L.y_stride;
+    o.status += k;
+    return o;
+}
+
 // validated, device-resident description of one batch
 struct Batch {
     int W = 0, n = 0, max_m = 0;
@@ -264,6 +293,8 @@ struct Batch {
     int nblocks[2][2] = {{0, 0}, {0, 0}};
     const int* rdesc[2] = {nullptr, nullptr};      // phase B: [lo, hi) block ranges to pre-sum, per level
     int nranges[2] = {0, 0};
+    // intraday block grid (for the pipelined upload): block k of level l ends at return row hf_off + (hf_bmin[l]+k+1)*hf_blk[l]
+    int hf_off = 0, hf_bmin[2] = {0, 0}, hf_blk[2] = {0, 0};
 };
 
 // Block grids of one phase, two levels (0 = coarse, 1 = fine; the fine size divides the coarse size): block b of
@@ -546,6 +577,8 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         bd += 2 * (size_t)nranges[l];
     }
     out->gdesc = h->desc + (size_t)7 * W;
+    out->hf_off = plan[0].off;
+    for (int l = 0; l < 2; ++l) { out->hf_bmin[l] = plan[0].bmin[l]; out->hf_blk[l] = plan[0].blk[l]; }
     out->resampled = rs;
     out->extra_row = rs ? h->desc + 5 * (size_t)W : nullptr;
     out->caps_row = h->desc + 6 * (size_t)W;
@@ -692,23 +725,26 @@ GramParams gram_params(const bp_handle* h, const Batch& B, const Layout& L, cons
     return g;
 }
 
-// block precompute: the Gram tile of every whole block of a phase / level, written fragment-major into its store
-int run_block_precompute(bp_handle* h, const Batch& B, int ph) {
+// block precompute: the Gram tile of the whole blocks [k0[l], k1[l]) of a phase / level (default: all of them),
+// written fragment-major into its store
+int run_block_precompute(bp_handle* h, const Batch& B, int ph, const int* k0 = nullptr, const int* k1 = nullptr) {
+    const int nt = (h->N + GRAM_TILE - 1) / GRAM_TILE;
+    const size_t tile_doubles = (size_t)(nt * (nt + 1) / 2) * GRAM_BLOCK_TILE_DOUBLES;
     for (int l = 0; l < 2; ++l) {
-        if (B.nblocks[ph][l] <= 0) continue;
+        const int b0 = k0 ? k0[l] : 0, b1 = k1 ? k1[l] : B.nblocks[ph][l];
+        if (b1 <= b0) continue;
         GramParams g{};
-        g.n_windows = B.nblocks[ph][l];
+        g.n_windows = b1 - b0;
         g.n_assets = h->N;
-        g.desc = B.bdesc[ph][l];
+        g.desc = B.bdesc[ph][l] + (size_t)b0 * GRAM_DESC_INTS;
         g.use_phaseA = ph == 0;
         g.use_phaseB = ph == 1;
         g.tile_store_out = 1;
-        g.out = h->store[ph][l];
+        g.out = h->store[ph][l] + (size_t)b0 * tile_doubles;
         StageTimer tm(h, BP_STAGE_GRAM);
         CU_TRY(launch_gram(g, h->map_hf, h->map_d, h->sm_count, h->stream));
         h->launches++;
         if (ph == 1 && B.nranges[l] > 0) {
-            const int nt = (h->N + GRAM_TILE - 1) / GRAM_TILE;
             launch_range_sum(h->store[1][l], B.rdesc[l], B.nranges[l], nt * (nt + 1) / 2, h->rstore[l], h->stream);
             h->launches++;
             CU_TRY(cudaGetLastError());
@@ -738,9 +774,13 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
     int rc = upload_batch(h, b, mode == BP_MODE_CONJUGATE, &B);
     if (rc) return rc;
     CU_TRY(cudaSetDevice(h->device));
-    if (mode == BP_MODE_CONJUGATE && (rc = wait_hf(h))) return rc;
     const Layout L = make_layout(h, B.max_m);
     int Wc = (int)std::min<size_t>((size_t)B.W, std::max<size_t>(1, h->ws_limit / L.per_window));
+    // Pipelined against a segmented asynchronous intraday upload: prep + Gram of the windows whose bars have
+    // arrived run while the rest is still being copied; the solve follows for all windows at once.
+    const bool pipelined = mode == BP_MODE_CONJUGATE && h->hf_pending && h->n_seg > 1 && h->seg_waited < h->n_seg &&
+                           solve && !out->T && !out->S0 && Wc >= B.W;
+    if (mode == BP_MODE_CONJUGATE && !pipelined && (rc = wait_hf(h))) return rc;
     rc = ensure_ws(h, (size_t)Wc * L.per_window + 256);
     if (rc) return rc;
     const Chunk c = carve(h->ws, L, Wc);
@@ -749,19 +789,61 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
         return fail(BP_ERR_INVALID, "risk_aversion must be non-zero");
 
     const bool any_gram = out->T || out->S0 || out->S1 || solve;
-    if (any_gram) {
+    if (any_gram && !pipelined) {
         if (mode == BP_MODE_CONJUGATE && (out->S0 || out->S1 || solve) && (rc = run_block_precompute(h, B, 0))) return rc;
         if ((out->T || out->S1 || solve) && (rc = run_block_precompute(h, B, 1))) return rc;
+    }
+    if (pipelined) {
+        if ((rc = run_block_precompute(h, B, 1))) return rc;          // daily blocks do not wait for the bars
+        int w_done = 0, k_done[2] = {0, 0};
+        for (int s = h->seg_waited; s < h->n_seg; ++s) {
+            CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_seg[s], 0));
+            const bool last = s == h->n_seg - 1;
+            const long long r_end = h->seg_end[s];
+            launch_log_returns(h->hf_prices, h->N, h->lr_hf, h->ld, r_end, h->N, h->sm_count, h->stream, h->lr_hf_done);
+            h->launches++;
+            CU_TRY(cudaGetLastError());
+            h->lr_hf_done = r_end;
+            int k_ready[2];
+            for (int l = 0; l < 2; ++l) {
+                k_ready[l] = B.nblocks[0][l];
+                if (!last && B.hf_blk[l] > 0) {
+                    const long long k = floor_div(r_end - B.hf_off, B.hf_blk[l]) - B.hf_bmin[l];
+                    k_ready[l] = (int)std::min<long long>(B.nblocks[0][l], std::max<long long>(k, k_done[l]));
+                }
+            }
+            if ((rc = run_block_precompute(h, B, 0, k_done, k_ready))) return rc;
+            k_done[0] = k_ready[0];
+            k_done[1] = k_ready[1];
+            int w_end = w_done;
+            if (last) w_end = B.W;
+            else while (w_end < B.W && (long long)b->hf_hi[w_end] <= r_end) ++w_end;
+            if (w_end > w_done) {
+                const Chunk cw = chunk_at(c, L, w_done);
+                PrepParams pp = prep_params(h, b, B, L, cw, w_done, mode);
+                {
+                    StageTimer tm(h, BP_STAGE_PREP);
+                    CU_TRY(launch_window_prep(pp, w_end - w_done, h->stream));
+                }
+                h->launches++;
+                if ((rc = run_gram(h, gram_params(h, B, L, cw, w_done, w_end - w_done, GRAM_S1), B.resampled))) return rc;
+                w_done = w_end;
+            }
+        }
+        h->seg_waited = h->n_seg;
+        h->hf_pending = false;
     }
     for (int w0 = 0; w0 < B.W; w0 += Wc) {
         const int wc = std::min(Wc, B.W - w0);
         const size_t ov = (size_t)w0 * N, om = (size_t)w0 * N * N;
-        PrepParams pp = prep_params(h, b, B, L, c, w0, mode);
-        {
-            StageTimer tm(h, BP_STAGE_PREP);
-            CU_TRY(launch_window_prep(pp, wc, h->stream));
+        if (!pipelined) {
+            PrepParams pp = prep_params(h, b, B, L, c, w0, mode);
+            {
+                StageTimer tm(h, BP_STAGE_PREP);
+                CU_TRY(launch_window_prep(pp, wc, h->stream));
+            }
+            h->launches++;
         }
-        h->launches++;
         if (out->T) {
             rc = run_gram(h, gram_params(h, B, L, c, w0, wc, GRAM_T), B.resampled);
             if (rc) return rc;
@@ -775,8 +857,10 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
             if (rc) return rc;
         }
         if (solve || out->S1) {
-            rc = run_gram(h, gram_params(h, B, L, c, w0, wc, mode == BP_MODE_CONJUGATE ? GRAM_S1 : GRAM_J), B.resampled);
-            if (rc) return rc;
+            if (!pipelined) {
+                rc = run_gram(h, gram_params(h, B, L, c, w0, wc, mode == BP_MODE_CONJUGATE ? GRAM_S1 : GRAM_J), B.resampled);
+                if (rc) return rc;
+            }
             rc = emit_sym(h, c.S, L, wc, out->S1 ? out->S1 + om : nullptr);
             if (rc) return rc;
         }
@@ -875,6 +959,8 @@ int bp_destroy(bp_handle* h) {
     cudaStreamDestroy(h->copy_stream);
     cudaEventDestroy(h->ev_main);
     cudaEventDestroy(h->ev_hf);
+    for (cudaEvent_t e : h->ev_seg)
+        if (e) cudaEventDestroy(e);
     cudaFree(h->desc);
     cudaFreeHost(h->desc_host);
     for (int a = 0; a < 2; ++a)
@@ -934,6 +1020,15 @@ int bp_get_gram_work(bp_handle* h, double* out4) {
 int bp_set_reuse_min_windows(bp_handle* h, int min_windows) {
     if (!h) return fail(BP_ERR_INVALID, "null handle");
     h->reuse_min_windows = min_windows;
+    return BP_OK;
+}
+
+int bp_set_upload_pipeline(bp_handle* h, int segments, long long min_bytes) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    if (segments < 1 || segments > bp_handle::MAX_SEG || min_bytes < 0)
+        return fail(BP_ERR_INVALID, "segments must be in [1,%d] and min_bytes >= 0", bp_handle::MAX_SEG);
+    h->pipe_segments = segments;
+    h->pipe_min_bytes = (size_t)min_bytes;
     return BP_OK;
 }
 
@@ -1034,10 +1129,25 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
     if (m->n_mcm > 0)
         CU_TRY(cudaMemcpyAsync(h->mcm, m->mcm, sizeof(double) * (size_t)m->n_mcm * D, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(h->rf_row, m->rf_row, sizeof(double) * (size_t)D, cudaMemcpyHostToDevice, st));
+    h->n_seg = 0;
+    h->seg_waited = 0;
+    h->lr_hf_done = 0;
     if (R > 0) {
-        CU_TRY(cudaMemcpyAsync(h->hf_prices, m->hf_prices, sizeof(double) * (size_t)R * N, cudaMemcpyHostToDevice, h->copy_stream));
-        launch_log_returns(h->hf_prices, N, h->lr_hf, ld, R, N, h->sm_count, h->copy_stream);
-        h->launches++;
+        // asynchronous uploads of a large block go in segments with an event each; the log returns of a segment
+        // are computed on the compute stream by its first consumer (wait_hf / the pipelined conjugate path)
+        int nseg = 1;
+        if (!blocking && sizeof(double) * (size_t)R * N >= h->pipe_min_bytes && R >= 64) nseg = h->pipe_segments;
+        for (int s = 0; s < nseg; ++s) {
+            const long long r0 = R * s / nseg, r1 = R * (s + 1) / nseg;
+            CU_TRY(cudaMemcpyAsync(h->hf_prices + (size_t)r0 * N, m->hf_prices + (size_t)r0 * N, sizeof(double) * (size_t)(r1 - r0) * N,
+                                   cudaMemcpyHostToDevice, h->copy_stream));
+            if (nseg > 1) {
+                if (!h->ev_seg[s]) CU_TRY(cudaEventCreateWithFlags(&h->ev_seg[s], cudaEventDisableTiming));
+                CU_TRY(cudaEventRecord(h->ev_seg[s], h->copy_stream));
+                h->seg_end[s] = r1;
+            }
+        }
+        h->n_seg = nseg > 1 ? nseg : 0;
         CU_TRY(cudaEventRecord(h->ev_hf, h->copy_stream));
         h->hf_pending = true;
     }

@@ -153,7 +153,7 @@ void launch_dense_prep(const DenseParams& p, bool jeffreys, cudaStream_t st);
 void launch_quadform(const double* S, int ldS, const double* w, int N, double* v_out, double n1, double inv_gamma,
                      double* nu, double* weights, cudaStream_t st);
 void launch_log_returns(const double* P, int ld_in, double* out, int ld_out, long long rows, int n_assets,
-                        int sm_count, cudaStream_t st);
+                        int sm_count, cudaStream_t st, long long row_begin = 0);
 size_t prep_smem_bytes(int n_window, int ldv);
 cudaError_t launch_window_prep(const PrepParams& p, int n_windows, cudaStream_t st);
 void launch_unpack_sym(const double* S, long long win_stride, int ldS, int N, int W, double* out, cudaStream_t st);

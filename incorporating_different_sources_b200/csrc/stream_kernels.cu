@@ -24,11 +24,11 @@ namespace bp {
 // TMA / vector-load layout), pad columns are written as zero.  One thread per pair of columns.
 template <bool VEC>
 __global__ void log_returns_kernel(const double* __restrict__ P, int ld_in, double* __restrict__ out, int ld_out,
-                                   long long rows, int n_assets) {
+                                   long long row_begin, long long rows, int n_assets) {
     const int half = ld_out >> 1;
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (c >= ld_out) return;
-    for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
+    for (long long r = row_begin + blockIdx.y; r < rows; r += gridDim.y) {
         double2 o = make_double2(0.0, 0.0);
         if (r > 0 && c < n_assets) {
             const double* cur = P + r * ld_in + c;
@@ -48,20 +48,21 @@ __global__ void log_returns_kernel(const double* __restrict__ P, int ld_in, doub
     (void)half;
 }
 
+// rows [row_begin, rows) of the return matrix (row 0 is the zero row; row r needs price rows r-1 and r)
 void launch_log_returns(const double* P, int ld_in, double* out, int ld_out, long long rows, int n_assets,
-                        int sm_count, cudaStream_t st) {
-    if (rows <= 0) return;
+                        int sm_count, cudaStream_t st, long long row_begin) {
+    if (rows <= row_begin) return;
     const int threads = 128;
     const int bx = (ld_out / 2 + threads - 1) / threads;
-    long long by = rows;
+    long long by = rows - row_begin;
     const long long cap = (long long)sm_count * 32 / bx + 1;
     if (by > cap) by = cap;
     if (by > 65535) by = 65535;
     dim3 grid(bx, (unsigned)by);
     if ((ld_in & 1) == 0)
-        log_returns_kernel<true><<<grid, threads, 0, st>>>(P, ld_in, out, ld_out, rows, n_assets);
+        log_returns_kernel<true><<<grid, threads, 0, st>>>(P, ld_in, out, ld_out, row_begin, rows, n_assets);
     else
-        log_returns_kernel<false><<<grid, threads, 0, st>>>(P, ld_in, out, ld_out, rows, n_assets);
+        log_returns_kernel<false><<<grid, threads, 0, st>>>(P, ld_in, out, ld_out, row_begin, rows, n_assets);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -131,6 +131,12 @@ class BayesEngine:
         if rc:
             _raise(rc)
 
+    def set_upload_pipeline(self, segments: int = 8, min_bytes: int = 256 << 20):
+        """Segments of an asynchronous intraday upload (1 disables) and the smallest block that is segmented."""
+        rc = self._lib.bp_set_upload_pipeline(self._h, int(segments), int(min_bytes))
+        if rc:
+            _raise(rc)
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.bp_launch_count(self._h))
