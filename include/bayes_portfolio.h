@@ -130,6 +130,11 @@ int bp_destroy(bp_handle* h);
 /* Launch on the caller's CUDA stream (a cudaStream_t), e.g. torch's current stream. */
 int bp_set_stream(bp_handle* h, void* cuda_stream);
 int bp_synchronize(bp_handle* h);
+/* With enable != 0 the batched calls return as soon as their work is queued even when the outputs are HOST
+ * buffers (which must then be page-locked): the results are complete after bp_synchronize().  Lets the host
+ * plan the next batch (e.g. the conjugate windows) while the GPU still works on the previous one (Jeffreys).
+ * Default 0: calls with host outputs return with the results in place. */
+int bp_set_async_outputs(bp_handle* h, int enable);
 /* Upper bound for the per-batch workspace (bytes); windows are processed in chunks that fit. */
 int bp_set_workspace_limit(bp_handle* h, size_t bytes);
 int bp_device_info(bp_handle* h, int* sm_count, size_t* free_bytes, size_t* total_bytes);
@@ -149,7 +154,7 @@ int bp_get_gram_work(bp_handle* h, double* out4);
  * windows; INT_MAX disables the reuse (every window is contracted from scratch). Default 32. */
 int bp_set_reuse_min_windows(bp_handle* h, int min_windows);
 /* Pipelining of bp_upload_market_async against bp_conjugate_batched: an intraday block of at least min_bytes
- * is copied in `segments` pieces (1..8; 1 disables), each followed by its log returns, and the conjugate
+ * is copied in `segments` pieces (1..8; 1 disables; geometric: 1/2, 1/4, ... of the rows), and the conjugate
  * statistics / Gram stages of the windows whose bars have arrived run while the rest is still on the bus
  * (the per-date loop of the reference, main.py:74 -> portfolio_calculations.py:1127, has no such ordering
  * constraint: every date only reads bars up to that date).  Default: 8 segments from 256 MiB. */

@@ -23,7 +23,7 @@ EXPORTED = [
     "bp_prepare_market", "bp_stats_batched", "bp_hf_cov_batched", "bp_conjugate_batched",
     "bp_jeffreys_batched", "bp_set_stage_timing", "bp_get_stage_times",
     "bp_excess_returns", "bp_quadratic_form", "bp_dense_posterior", "bp_moments_batched",
-    "bp_upload_market_async", "bp_backtest_batched", "bp_get_gram_work", "bp_set_reuse_min_windows", "bp_set_upload_pipeline",
+    "bp_upload_market_async", "bp_backtest_batched", "bp_get_gram_work", "bp_set_reuse_min_windows", "bp_set_upload_pipeline", "bp_set_async_outputs",
     "bp_set_resampled",
 ]
 BP_NSTAGE = 8
@@ -123,6 +123,7 @@ def load():
     lib.bp_get_gram_work.argtypes = [C.c_void_p, c_double_p]
     lib.bp_set_reuse_min_windows.argtypes = [C.c_void_p, C.c_int]
     lib.bp_set_upload_pipeline.argtypes = [C.c_void_p, C.c_int, C.c_longlong]
+    lib.bp_set_async_outputs.argtypes = [C.c_void_p, C.c_int]
     lib.bp_backtest_batched.argtypes = [C.c_void_p, C.POINTER(BacktestDesc)]
     lib.bp_excess_returns.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.c_void_p]
     lib.bp_quadratic_form.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -91,6 +91,15 @@ struct bp_handle {
     int* desc = nullptr;
     int* desc_host = nullptr;          // page-locked staging of the descriptors (read zero-copy by a kernel)
     size_t desc_cap = 0;               // capacity in ints
+    // two descriptor slots used alternately: planning the next batch on the host never waits for the GPU to
+    // have fetched (or finished using) the previous one, only for the batch before that
+    int* desc_slot[2] = {nullptr, nullptr};
+    int* desc_host_slot[2] = {nullptr, nullptr};
+    size_t desc_cap_slot[2] = {0, 0};
+    cudaEvent_t ev_desc[2] = {nullptr, nullptr};
+    bool ev_desc_armed[2] = {false, false};
+    int desc_turn = 0;
+    bool async_outputs = false;        // host outputs are complete only after bp_synchronize (see bp_set_async_outputs)
     // block tile stores of the Gram kernel (window-overlap reuse) and the smallest batch that uses them
     double* store[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [phase][level]
     size_t store_cap[2][2] = {{0, 0}, {0, 0}};                           // capacity in doubles
@@ -480,19 +489,27 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
     const int nb_total = plan[0].nb[0] + plan[0].nb[1] + plan[1].nb[0] + plan[1].nb[1];
     const size_t ints_needed = (size_t)(7 + GRAM_DESC_INTS) * W + (size_t)GRAM_DESC_INTS * nb_total +
                                2 * (size_t)(nranges[0] + nranges[1]);
-    if (ints_needed > h->desc_cap) {
-        if (h->desc) {
-            CU_TRY(cudaStreamSynchronize(h->stream));
-            cudaFree(h->desc);
-            cudaFreeHost(h->desc_host);
-        }
-        h->desc = nullptr;
-        h->desc_host = nullptr;
-        h->desc_cap = 0;
-        CU_TRY(cudaMalloc(&h->desc, sizeof(int) * ints_needed));
-        CU_TRY(cudaHostAlloc(&h->desc_host, sizeof(int) * ints_needed, cudaHostAllocDefault));
-        h->desc_cap = ints_needed;
+    const int slot = h->desc_turn ^= 1;
+    if (h->ev_desc_armed[slot]) {
+        CU_TRY(cudaEventSynchronize(h->ev_desc[slot]));      // its staging buffer has been fetched
+        h->ev_desc_armed[slot] = false;
     }
+    if (ints_needed > h->desc_cap_slot[slot]) {
+        if (h->desc_slot[slot]) {
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            cudaFree(h->desc_slot[slot]);
+            cudaFreeHost(h->desc_host_slot[slot]);
+        }
+        h->desc_slot[slot] = nullptr;
+        h->desc_host_slot[slot] = nullptr;
+        h->desc_cap_slot[slot] = 0;
+        CU_TRY(cudaMalloc(&h->desc_slot[slot], sizeof(int) * ints_needed));
+        CU_TRY(cudaHostAlloc(&h->desc_host_slot[slot], sizeof(int) * ints_needed, cudaHostAllocDefault));
+        h->desc_cap_slot[slot] = ints_needed;
+    }
+    h->desc = h->desc_slot[slot];
+    h->desc_host = h->desc_host_slot[slot];
+    h->desc_cap = h->desc_cap_slot[slot];
     int* host = h->desc_host;
     memset(host, 0, sizeof(int) * ints_needed);
     int* gd = host + (size_t)7 * W;                  // Gram job descriptors
@@ -583,11 +600,13 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
     out->extra_row = rs ? h->desc + 5 * (size_t)W : nullptr;
     out->caps_row = h->desc + 6 * (size_t)W;
     // zero-copy fetch by a kernel on the compute stream (not the copy engine, see fetch_ints_kernel); the
-    // staging buffer is reused by the next call, so wait until it has been consumed
+    // staging buffer of this slot is rewritten two batches later, after this event
     launch_fetch_ints(host, h->desc, (long long)ints_needed, h->stream);
     h->launches++;
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (!h->ev_desc[slot]) CU_TRY(cudaEventCreateWithFlags(&h->ev_desc[slot], cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(h->ev_desc[slot], h->stream));
+    h->ev_desc_armed[slot] = true;
     if (need_hf && b->prior_n) {
         if (W > h->prior_n_cap) {
             cudaFree(h->prior_n);
@@ -761,7 +780,7 @@ int run_gram(bp_handle* h, const GramParams& g, bool resampled) {
 }
 
 int finish(bp_handle* h) {
-    if (h->need_sync) {
+    if (h->need_sync && !h->async_outputs) {
         CU_TRY(cudaStreamSynchronize(h->stream));
         h->need_sync = false;
     }
@@ -961,8 +980,11 @@ int bp_destroy(bp_handle* h) {
     cudaEventDestroy(h->ev_hf);
     for (cudaEvent_t e : h->ev_seg)
         if (e) cudaEventDestroy(e);
-    cudaFree(h->desc);
-    cudaFreeHost(h->desc_host);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(h->desc_slot[k]);
+        cudaFreeHost(h->desc_host_slot[k]);
+        if (h->ev_desc[k]) cudaEventDestroy(h->ev_desc[k]);
+    }
     for (int a = 0; a < 2; ++a)
         for (int l = 0; l < 2; ++l) cudaFree(h->store[a][l]);
     cudaFree(h->rstore[0]);
@@ -985,6 +1007,17 @@ int bp_synchronize(bp_handle* h) {
     if (!h) return fail(BP_ERR_INVALID, "null handle");
     CU_TRY(cudaStreamSynchronize(h->copy_stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
+    h->need_sync = false;
+    return BP_OK;
+}
+
+int bp_set_async_outputs(bp_handle* h, int enable) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    if (!enable && h->need_sync) {
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        h->need_sync = false;
+    }
+    h->async_outputs = enable != 0;
     return BP_OK;
 }
 
@@ -1137,8 +1170,12 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
         // are computed on the compute stream by its first consumer (wait_hf / the pipelined conjugate path)
         int nseg = 1;
         if (!blocking && sizeof(double) * (size_t)R * N >= h->pipe_min_bytes && R >= 64) nseg = h->pipe_segments;
+        // geometric segments (1/2, 1/4, ... of the rows): whatever the compute stream is busy with when the copy
+        // starts, little work is left to do after the LAST segment has arrived
+        long long r1 = 0;
         for (int s = 0; s < nseg; ++s) {
-            const long long r0 = R * s / nseg, r1 = R * (s + 1) / nseg;
+            const long long r0 = r1;
+            r1 = s == nseg - 1 ? R : std::max(r0, R - (R >> (s + 1)));
             CU_TRY(cudaMemcpyAsync(h->hf_prices + (size_t)r0 * N, m->hf_prices + (size_t)r0 * N, sizeof(double) * (size_t)(r1 - r0) * N,
                                    cudaMemcpyHostToDevice, h->copy_stream));
             if (nseg > 1) {

@@ -131,6 +131,13 @@ class BayesEngine:
         if rc:
             _raise(rc)
 
+    def set_async_outputs(self, enable: bool):
+        """Batched calls with page-locked HOST outputs (``into=``) return once queued; results are complete after
+        ``synchronize()``.  The host can then plan the next batch while the GPU works on the previous one."""
+        rc = self._lib.bp_set_async_outputs(self._h, int(bool(enable)))
+        if rc:
+            _raise(rc)
+
     def set_upload_pipeline(self, segments: int = 8, min_bytes: int = 256 << 20):
         """Segments of an asynchronous intraday upload (1 disables) and the smallest block that is segmented."""
         rc = self._lib.bp_set_upload_pipeline(self._h, int(segments), int(min_bytes))

@@ -239,6 +239,39 @@ def test_gpu_pipelined_upload_matches_blocking(engine, segments, order):
     finally:
         engine.set_upload_pipeline()
 
+def test_gpu_async_outputs_match_blocking(engine):
+    """bp_set_async_outputs: batched calls with page-locked host outputs return once queued (so the host plans the
+    conjugate batch while the GPU runs Jeffreys); after synchronize() the buffers hold the blocking results.
+    Three batches in a row cycle both descriptor slots."""
+    import torch
+    from incorporating_different_sources_b200.engine import upload_synthetic
+    from incorporating_different_sources_b200.synthetic import generate_market
+    from incorporating_different_sources_b200.windows import plan_daily_windows
+    mkt = generate_market(30, 160, seed=29)
+    upload_synthetic(engine, mkt)
+    spec = dict(weighting_strategy="conjugate_hf_vix_vw", size=30, risk_aversion=5, rolling_window=60,
+                rolling_window_frequency="daily", mcm_scaling=1)
+    jspec = dict(spec, weighting_strategy="jeffreys")
+    d_idx = list(range(60, 160))
+    cb = plan_daily_windows(spec, mkt.dates, d_idx, mkt.hf_ts, hf_lookback_days=7)
+    jb = plan_daily_windows(jspec, mkt.dates, d_idx, need_hf=False)
+    jb2 = plan_daily_windows(dict(jspec, rolling_window=40), mkt.dates, d_idx, need_hf=False)
+    ref = [engine.jeffreys(jb, outputs=("weights", "status")), engine.conjugate(cb, outputs=("weights", "status")),
+           engine.jeffreys(jb2, outputs=("weights", "status"))]
+    W, N = len(d_idx), 30
+    bufs = [{"weights": torch.zeros(W, N, dtype=torch.float64).pin_memory().numpy(),
+             "status": torch.ones(W, dtype=torch.int32).pin_memory().numpy()} for _ in range(3)]
+    engine.set_async_outputs(True)
+    try:
+        engine.jeffreys(jb, outputs=("weights", "status"), into=bufs[0])
+        engine.conjugate(cb, outputs=("weights", "status"), into=bufs[1])
+        engine.jeffreys(jb2, outputs=("weights", "status"), into=bufs[2])
+        engine.synchronize()
+    finally:
+        engine.set_async_outputs(False)
+    for got, want in zip(bufs, ref):
+        assert np.array_equal(got["weights"], want["weights"]) and np.array_equal(got["status"], want["status"])
+
 
 @pytest.mark.parametrize("dates", ["consecutive", "every3rd", "random"])
 def test_gpu_window_overlap_reuse_matches_oracle(engine, dates):

@@ -20,7 +20,9 @@ cb = plan_daily_windows(conj, mkt.dates, d_idx, mkt.hf_ts, hf_lookback_days=7)
 jb = plan_daily_windows(jeff, mkt.dates, d_idx, need_hf=False)
 W, N = len(d_idx), 500
 hw_c, hw_cv = pin(np.zeros((W, N))); hw_j, hw_jv = pin(np.zeros((W, N)))
-hs_c = np.zeros(W, dtype=np.int32); hs_j = np.zeros(W, dtype=np.int32)
+hs_ct = torch.zeros(W, dtype=torch.int32).pin_memory(); hs_jt = torch.zeros(W, dtype=torch.int32).pin_memory()
+hs_c, hs_j = hs_ct.numpy(), hs_jt.numpy()
+eng.set_async_outputs(len(sys.argv) > 1 and sys.argv[1] == 'async')
 for it in range(4):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     eng.upload_market(**host, async_copy=True); t1 = time.perf_counter()
