@@ -7,23 +7,24 @@
 // by S = L L', L z = b, L' w = z (within 1.5e-12 of inv()*b on well-posed inputs) and
 // v1 = w1' S1 w1 = z'z.
 //
-// One CTA (4 warps) per window, 6 CTAs per SM (measured: 4 -> 29.7 ms, 6 -> 26.4 ms, 8 -> 26.5 ms per step), left-looking blocked factorisation with 32-column
-// panels, in place in the [rows][ldS] device layout produced by the Gram kernel (lower triangle):
+// One CTA (4 warps) per window, 6 CTAs per SM (measured with the first TMA version: 4 -> 29.7 ms, 6 -> 26.4 ms,
+// 8 -> 26.5 ms per step), left-looking blocked factorisation with 32-column panels, in place in the [rows][ldS] device layout produced by the Gram kernel (lower triangle):
 //   U  panel update   C = S[j0:, j0:j0+32] - L[j0:, :j0] L[j0:j0+32, :j0]'   on the FP64 tensor cores.
 //                     The already factored columns are streamed through shared memory by TMA
 //                     (2-D tensor map over the whole workspace, 32-row x 16-column boxes,
 //                     SWIZZLE_128B, 3-stage mbarrier ring) in slabs of 8*TPW m-tiles; each warp owns TPW
 //                     8-row m-tiles of the slab and all four 8-column n-tiles of the panel.
-//   F  diagonal block 32x32 right-looking Cholesky AND its triangular inverse in ONE 32-step loop by the
-//                     whole CTA in shared memory (one barrier per step; a single warp doing this alone is
-//                     latency bound and took 2/3 of the kernel).  The diagonal block lives in the first
-//                     slab, so F runs right after that slab's update.
+//   F  diagonal block 32x32, blocked by 8 in FRAGMENT space: after the first slab the four warps that own its
+//                     row blocks hold it in their accumulators; the warp owning a diagonal 8x8 tile computes its
+//                     Cholesky factor and inverse in registers (warp shuffles, potrf8_inv8), the warps below
+//                     solve / update their tiles with 2 DMMAs each.  (A single warp in shared memory was 2/3 of
+//                     the kernel, CTA-wide 32-step loops in shared memory still 1/4.)
 //   T  panel solve    L[j0+32:, j0:j0+32] = C * inv(L_d)' on the tensor cores, FUSED into the epilogue of
 //                     the panel update: the accumulator fragment of a DMMA is, column for column, a valid
 //                     A fragment (lane (g,tig) holds columns 8nt+2tig+h, which become the k slots of step
 //                     (nt,h)), so C never goes to memory: the accumulators start as -S, collect +L L',
-//                     are multiplied by inv(L_d)' from registers, and the finished factor rows are stored
-//                     once.  (The first version wrote C and re-read it in a separate T phase: 2 MB of DRAM
+//                     go through a block forward substitution against L_d (8x8 inverses on the diagonal)
+//                     in registers, and the finished factor rows are stored once.  (The first version wrote C and re-read it in a separate T phase: 2 MB of DRAM
 //                     traffic per window and 15% of the kernel.)
 // The factor is written with generic stores and re-read by TMA in later panels, so every panel ends
 // with fence.proxy.async + a block barrier.  The right-hand side rides along as one extra row
