@@ -110,6 +110,9 @@ struct bp_handle {
     double work_k_rows = 0, work_add_blocks = 0, work_pre_rows = 0, work_full_rows = 0;
     double* prior_n = nullptr;
     int prior_n_cap = 0;
+    // banded-GEMM daily pass (band_prep.cu): risk-free weights [W][band_ld] and their sums [W][2]
+    double *band_aw = nullptr, *band_stats = nullptr;
+    size_t band_aw_cap = 0, band_stats_cap = 0;
     // workspace
     unsigned char* ws = nullptr;
     size_t ws_bytes = 0;
@@ -302,6 +305,7 @@ struct Batch {
     int nblocks[2][2] = {{0, 0}, {0, 0}};
     const int* rdesc[2] = {nullptr, nullptr};      // phase B: [lo, hi) block ranges to pre-sum, per level
     int nranges[2] = {0, 0};
+    bool band_ok = false;              // consecutive trade dates: the daily pass runs as a banded GEMM
     // intraday block grid (for the pipelined upload): block k of level l ends at return row hf_off + (hf_bmin[l]+k+1)*hf_blk[l]
     int hf_off = 0, hf_bmin[2] = {0, 0}, hf_blk[2] = {0, 0};
 };
@@ -594,6 +598,14 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         bd += 2 * (size_t)nranges[l];
     }
     out->gdesc = h->desc + (size_t)7 * W;
+    {
+        // banded-GEMM daily pass: worth it when 32 consecutive windows share almost all of their rows
+        static const bool no_band = getenv("BP_NO_BAND") != nullptr;
+        bool ok = !no_band && !rs && W >= 32 && n >= 16;
+        for (int w = 1; ok && w < W; ++w) ok = b->day_row[w] >= b->day_row[w - 1];
+        if (ok) ok = (long long)b->day_row[W - 1] - b->day_row[0] <= 2LL * W;
+        out->band_ok = ok;
+    }
     out->hf_off = plan[0].off;
     for (int l = 0; l < 2; ++l) { out->hf_bmin[l] = plan[0].bmin[l]; out->hf_blk[l] = plan[0].blk[l]; }
     out->resampled = rs;
@@ -707,6 +719,10 @@ PrepParams prep_params(const bp_handle* h, const bp_window_batch* b, const Batch
     p.scal = c.scal;
     p.y_ws = c.y;
     p.y_stride = L.y_stride;
+    p.use_band = B.band_ok ? 1 : 0;
+    p.band_ld = round_up(B.n - 1, 2);
+    p.band_aw = B.band_ok ? h->band_aw + (size_t)w0 * p.band_ld : nullptr;
+    p.band_stats = B.band_ok ? h->band_stats + 2 * (size_t)w0 : nullptr;
     return p;
 }
 
@@ -804,6 +820,20 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
     if (rc) return rc;
     const Chunk c = carve(h->ws, L, Wc);
     const int N = h->N;
+    if (B.band_ok) {
+        const size_t need_aw = (size_t)B.W * round_up(B.n - 1, 2), need_st = 2 * (size_t)B.W;
+        if (need_aw > h->band_aw_cap || need_st > h->band_stats_cap) {
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            cudaFree(h->band_aw);
+            cudaFree(h->band_stats);
+            h->band_aw = h->band_stats = nullptr;
+            h->band_aw_cap = h->band_stats_cap = 0;
+            CU_TRY(cudaMalloc(&h->band_aw, sizeof(double) * need_aw));
+            CU_TRY(cudaMalloc(&h->band_stats, sizeof(double) * need_st));
+            h->band_aw_cap = need_aw;
+            h->band_stats_cap = need_st;
+        }
+    }
     if (solve && mode == BP_MODE_CONJUGATE && !(b->risk_aversion != 0.0))
         return fail(BP_ERR_INVALID, "risk_aversion must be non-zero");
 
@@ -842,7 +872,8 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
                 PrepParams pp = prep_params(h, b, B, L, cw, w_done, mode);
                 {
                     StageTimer tm(h, BP_STAGE_PREP);
-                    CU_TRY(launch_window_prep(pp, w_end - w_done, h->stream));
+                    CU_TRY(launch_window_prep(pp, w_end - w_done, h->stream, h->D));
+                    h->launches += pp.use_band ? 2 : 0;
                 }
                 h->launches++;
                 if ((rc = run_gram(h, gram_params(h, B, L, cw, w_done, w_end - w_done, GRAM_S1), B.resampled))) return rc;
@@ -859,7 +890,8 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
             PrepParams pp = prep_params(h, b, B, L, c, w0, mode);
             {
                 StageTimer tm(h, BP_STAGE_PREP);
-                CU_TRY(launch_window_prep(pp, wc, h->stream));
+                CU_TRY(launch_window_prep(pp, wc, h->stream, h->D));
+                h->launches += pp.use_band ? (mode == BP_MODE_JEFFREYS ? 1 : 2) : 0;
             }
             h->launches++;
         }
@@ -990,6 +1022,8 @@ int bp_destroy(bp_handle* h) {
     cudaFree(h->rstore[0]);
     cudaFree(h->rstore[1]);
     cudaFree(h->prior_n);
+    cudaFree(h->band_aw);
+    cudaFree(h->band_stats);
     cudaFree(h->ws);
     cudaFree(h->stage);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);

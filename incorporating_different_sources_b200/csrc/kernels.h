@@ -56,6 +56,11 @@ struct PrepParams {
     double* scal;             // [W][BP_NSCAL]
     double* y_ws;             // [W][y_stride] scratch for the HF row dots
     long long y_stride;
+    // banded-GEMM form of the daily pass (band_prep.cu), used for batches of consecutive trade dates
+    int use_band;
+    double* band_aw;          // [W][band_ld] risk-free weights a_k(w)
+    int band_ld;
+    double* band_stats;       // [W][2] sum a, sum a^2
 };
 
 // Per-window job descriptor of the Gram kernel (GRAM_DESC_INTS ints), 10 per phase (A = intraday, scaled by
@@ -155,7 +160,8 @@ void launch_quadform(const double* S, int ldS, const double* w, int N, double* v
 void launch_log_returns(const double* P, int ld_in, double* out, int ld_out, long long rows, int n_assets,
                         int sm_count, cudaStream_t st, long long row_begin = 0);
 size_t prep_smem_bytes(int n_window, int ldv);
-cudaError_t launch_window_prep(const PrepParams& p, int n_windows, cudaStream_t st);
+cudaError_t launch_window_prep(const PrepParams& p, int n_windows, cudaStream_t st, long long n_daily_rows = 0);
+cudaError_t launch_daily_band(const PrepParams& p, int n_windows, long long n_rows, cudaStream_t st);
 void launch_unpack_sym(const double* S, long long win_stride, int ldS, int N, int W, double* out, cudaStream_t st);
 void launch_unpack_vec(const double* v, int ldv, int N, long long W, double* out, cudaStream_t st);
 

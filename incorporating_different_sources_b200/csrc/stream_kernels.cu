@@ -147,10 +147,15 @@ __global__ void __launch_bounds__(PREP_THREADS, 3) window_prep_kernel(PrepParams
     const int caps_row = p.caps_row ? p.caps_row[w] : day_row;
     double* scal = p.scal + (long long)w * BP_S_COUNT;
 
+    double sa = 0.0, saa = 0.0;
+    double2 sum[NCH], wsum[NCH];
+    if (p.use_band) {
+        // t, p (and sum a) were produced by the banded-GEMM form of this pass (band_prep.cu)
+        sa = p.band_stats[2 * (long long)w];
+    } else {
     // ---- a_k = (1 + rf)^(gbar/365) - 1  (:40-48); gbar = calendar span / (n-1)
     const double gbar = (double)p.span_days[w] / (double)K;
     const double expo = gbar / 365.0;
-    double sa = 0.0, saa = 0.0;
     for (int k = tid; k < K; k += PREP_THREADS) {
         const long long rr = k < K1 ? r0 + k : (long long)extra_row;
         const double a = pow(1.0 + p.rf_row[rr], expo) - 1.0;
@@ -161,7 +166,6 @@ __global__ void __launch_bounds__(PREP_THREADS, 3) window_prep_kernel(PrepParams
     sa = block_sum(sa, scratch);
     saa = block_sum(saa, scratch);
 
-    double2 sum[NCH], wsum[NCH];
     // ---- daily column sums: t = L'1 - (sum a),  p = L'a - (a'a)/2
     for (int col0 = 0; col0 < p.ldv; col0 += 512) {
         col_accumulate<false>(p.lr_daily, p.ld, r0, K1, col0, a_s, nullptr, nullptr, false, sum, wsum);
@@ -185,6 +189,7 @@ __global__ void __launch_bounds__(PREP_THREADS, 3) window_prep_kernel(PrepParams
                 *reinterpret_cast<double2*>(p.rhs + (long long)w * p.ldv + c) = tv;
             }
         }
+    }
     }
     if (p.mode == BP_MODE_JEFFREYS) {
         if (tid == 0) {
@@ -297,8 +302,12 @@ size_t prep_smem_bytes(int n_window, int ldv) {
     return sizeof(double) * (size_t)(((K + 1) & ~1) + ldv + PREP_WARPS * 512 + 40);
 }
 
-cudaError_t launch_window_prep(const PrepParams& p, int n_windows, cudaStream_t st) {
+cudaError_t launch_window_prep(const PrepParams& p, int n_windows, cudaStream_t st, long long n_daily_rows) {
     if (n_windows <= 0) return cudaSuccess;
+    if (p.use_band) {
+        cudaError_t eb = launch_daily_band(p, n_windows, n_daily_rows, st);
+        if (eb != cudaSuccess || p.mode == BP_MODE_JEFFREYS) return eb;      // Jeffreys needs nothing else
+    }
     const size_t smem = prep_smem_bytes(p.n_window, p.ldv);
     cudaError_t e = cudaFuncSetAttribute(window_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
