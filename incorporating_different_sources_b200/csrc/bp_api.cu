@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -105,6 +106,8 @@ struct bp_handle {
     size_t store_cap[2][2] = {{0, 0}, {0, 0}};                           // capacity in doubles
     double* rstore[2] = {nullptr, nullptr};                              // phase-B range-sum stores [level]
     size_t rstore_cap[2] = {0, 0};
+    double* fstore = nullptr;                                            // phase-B combined runs (coarse + fine + fine)
+    size_t fstore_cap = 0;
     int reuse_min_windows = 32;
     // work counters of the Gram stage since the last bp_get_gram_work (bench.py's roofline accounting)
     double work_k_rows = 0, work_add_blocks = 0, work_pre_rows = 0, work_full_rows = 0;
@@ -305,6 +308,8 @@ struct Batch {
     int nblocks[2][2] = {{0, 0}, {0, 0}};
     const int* rdesc[2] = {nullptr, nullptr};      // phase B: [lo, hi) block ranges to pre-sum, per level
     int nranges[2] = {0, 0};
+    const int* fdesc = nullptr;                    // phase B: [coarse, fineA, fineB] run ids to combine
+    int nfull = 0;
     bool band_ok = false;              // consecutive trade dates: the daily pass runs as a banded GEMM
     // intraday block grid (for the pipelined upload): block k of level l ends at return row hf_off + (hf_bmin[l]+k+1)*hf_blk[l]
     int hf_off = 0, hf_bmin[2] = {0, 0}, hf_blk[2] = {0, 0};
@@ -439,6 +444,9 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
     // phase B (daily rows): the run of whole blocks inside a window is the same for many consecutive windows, so
     // each distinct run [lo, hi) is summed once (range_sum_kernel) and a window adds one tile per run
     std::map<std::pair<long long, long long>, int> range_id[2];
+    // ... and the (coarse, fine, fine) run triple of a window is combined once per distinct triple (combine_runs_kernel)
+    typedef std::array<long long, 6> RunKey;
+    std::map<RunKey, int> full_id;
     // first pass: block ranges touched by the windows, per level
     for (int ph = 0; ph < 2; ++ph) {
         if (plan[ph].blk[0] <= 0 && plan[ph].blk[1] <= 0) continue;
@@ -455,6 +463,8 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
                 if (sp.c_hi > sp.c_lo) range_id[0].emplace(std::make_pair(sp.c_lo, sp.c_hi), 0);
                 if (sp.fa_hi > sp.fa_lo) range_id[1].emplace(std::make_pair(sp.fa_lo, sp.fa_hi), 0);
                 if (sp.fb_hi > sp.fb_lo) range_id[1].emplace(std::make_pair(sp.fb_lo, sp.fb_hi), 0);
+                if (sp.c_hi > sp.c_lo || sp.fa_hi > sp.fa_lo || sp.fb_hi > sp.fb_lo)
+                    full_id.emplace(RunKey{sp.c_lo, sp.c_hi, sp.fa_lo, sp.fa_hi, sp.fb_lo, sp.fb_hi}, 0);
             }
         }
         for (int l = 0; l < 2; ++l) {
@@ -490,9 +500,23 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             h->rstore_cap[l] = need;
         }
     }
+    int nfull = 0;
+    if (plan[1].blk[0] <= 0 && plan[1].blk[1] <= 0) full_id.clear();
+    for (auto& kv : full_id) kv.second = nfull++;
+    {
+        const size_t need = (size_t)nfull * npairs_t * GRAM_BLOCK_TILE_DOUBLES;
+        if (need > h->fstore_cap) {
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            cudaFree(h->fstore);
+            h->fstore = nullptr;
+            h->fstore_cap = 0;
+            CU_TRY(cudaMalloc(&h->fstore, need * sizeof(double)));
+            h->fstore_cap = need;
+        }
+    }
     const int nb_total = plan[0].nb[0] + plan[0].nb[1] + plan[1].nb[0] + plan[1].nb[1];
     const size_t ints_needed = (size_t)(7 + GRAM_DESC_INTS) * W + (size_t)GRAM_DESC_INTS * nb_total +
-                               2 * (size_t)(nranges[0] + nranges[1]);
+                               2 * (size_t)(nranges[0] + nranges[1]) + 3 * (size_t)nfull;
     const int slot = h->desc_turn ^= 1;
     if (h->ev_desc_armed[slot]) {
         CU_TRY(cudaEventSynchronize(h->ev_desc[slot]));      // its staging buffer has been fetched
@@ -559,9 +583,12 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             int* dB = gd + (size_t)w * GRAM_DESC_INTS + GRAM_PHASE_INTS;
             write_phase_desc(sp, plan[1], dB);
             // one pre-summed tile per run of whole blocks
-            if (dB[5] > 0) { dB[4] = range_id[0][std::make_pair(sp.c_lo, sp.c_hi)]; dB[5] = 1; }
-            if (dB[7] > 0) { dB[6] = range_id[1][std::make_pair(sp.fa_lo, sp.fa_hi)]; dB[7] = 1; }
-            if (dB[9] > 0) { dB[8] = range_id[1][std::make_pair(sp.fb_lo, sp.fb_hi)]; dB[9] = 1; }
+            // ... combined into one tile per distinct (coarse, fine, fine) triple: the coarse slot points into fstore
+            if (dB[5] > 0 || dB[7] > 0 || dB[9] > 0) {
+                dB[4] = full_id[RunKey{sp.c_lo, sp.c_hi, sp.fa_lo, sp.fa_hi, sp.fb_lo, sp.fb_hi}];
+                dB[5] = 1;
+                dB[6] = dB[7] = dB[8] = dB[9] = 0;
+            }
         }
         const int* d = gd + (size_t)w * GRAM_DESC_INTS;
         auto r8 = [](int r) { return (r + 7) / 8 * 8; };
@@ -597,6 +624,16 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         out->nranges[l] = nranges[l];
         bd += 2 * (size_t)nranges[l];
     }
+    for (const auto& kv : full_id) {
+        const RunKey& k = kv.first;
+        int* d = bd + 3 * (size_t)kv.second;
+        d[0] = k[1] > k[0] ? range_id[0][std::make_pair(k[0], k[1])] : -1;
+        d[1] = k[3] > k[2] ? range_id[1][std::make_pair(k[2], k[3])] : -1;
+        d[2] = k[5] > k[4] ? range_id[1][std::make_pair(k[4], k[5])] : -1;
+    }
+    out->fdesc = nfull ? h->desc + (bd - host) : nullptr;
+    out->nfull = nfull;
+    bd += 3 * (size_t)nfull;
     out->gdesc = h->desc + (size_t)7 * W;
     {
         // banded-GEMM daily pass: worth it when 32 consecutive windows share almost all of their rows
@@ -741,7 +778,7 @@ GramParams gram_params(const bp_handle* h, const Batch& B, const Layout& L, cons
     g.desc = B.gdesc + (size_t)w0 * GRAM_DESC_INTS;
     for (int l = 0; l < 2; ++l) {
         g.store[0][l] = h->store[0][l];          // intraday: one tile per whole block
-        g.store[1][l] = h->rstore[l];            // daily: one pre-summed tile per run of whole blocks
+        g.store[1][l] = l == 0 ? h->fstore : h->rstore[l];      // daily: ONE combined tile per window (runs of whole blocks, pre-summed)
     }
     const bool hf = kind == GRAM_S0 || kind == GRAM_S1;
     const bool daily = kind != GRAM_S0;
@@ -784,6 +821,12 @@ int run_block_precompute(bp_handle* h, const Batch& B, int ph, const int* k0 = n
             h->launches++;
             CU_TRY(cudaGetLastError());
         }
+    }
+    if (ph == 1 && !k0 && B.nfull > 0) {
+        StageTimer tm(h, BP_STAGE_GRAM);
+        launch_combine_runs(h->rstore[0], h->rstore[1], B.fdesc, B.nfull, nt * (nt + 1) / 2, h->fstore, h->stream);
+        h->launches++;
+        CU_TRY(cudaGetLastError());
     }
     return BP_OK;
 }
@@ -1021,6 +1064,7 @@ int bp_destroy(bp_handle* h) {
         for (int l = 0; l < 2; ++l) cudaFree(h->store[a][l]);
     cudaFree(h->rstore[0]);
     cudaFree(h->rstore[1]);
+    cudaFree(h->fstore);
     cudaFree(h->prior_n);
     cudaFree(h->band_aw);
     cudaFree(h->band_stats);

@@ -410,6 +410,42 @@ void launch_range_sum(const double* store, const int* ranges, int n_ranges, int 
     range_sum_kernel<<<grid, 256, 0, st>>>(store, ranges, npairs, out);
 }
 
+// One tile per distinct RUN TRIPLE (coarse run + fine run on the head side + fine run on the tail side): the three
+// pre-summed run tiles of a window's daily rows are added up once per distinct triple (it changes only when a
+// window edge crosses a fine-block boundary), so a window adds ONE tile per output tile instead of three.
+// triples = [coarse_id, fineA_id, fineB_id] per output, -1 = absent.  Order: coarse + fineA + fineB (deterministic).
+__global__ void combine_runs_kernel(const double* __restrict__ rs_coarse, const double* __restrict__ rs_fine,
+                                    const int* __restrict__ triples, int npairs, double* __restrict__ out) {
+    const int r = blockIdx.y;
+    const int ic = triples[3 * r], ia = triples[3 * r + 1], ib = triples[3 * r + 2];
+    const long long per_block = (long long)npairs * (GRAM_BLOCK_TILE_DOUBLES / 2);
+    const double2* sc = reinterpret_cast<const double2*>(rs_coarse);
+    const double2* sf = reinterpret_cast<const double2*>(rs_fine);
+    double2* dst = reinterpret_cast<double2*>(out) + (long long)r * per_block;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_block; i += (long long)gridDim.x * blockDim.x) {
+        double2 acc = make_double2(0.0, 0.0);
+        if (ic >= 0) acc = sc[(long long)ic * per_block + i];
+        if (ia >= 0) {
+            const double2 v = sf[(long long)ia * per_block + i];
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+        if (ib >= 0) {
+            const double2 v = sf[(long long)ib * per_block + i];
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+        dst[i] = acc;
+    }
+}
+
+void launch_combine_runs(const double* rs_coarse, const double* rs_fine, const int* triples, int n, int npairs,
+                         double* out, cudaStream_t st) {
+    if (n <= 0) return;
+    dim3 grid(64, n);
+    combine_runs_kernel<<<grid, 256, 0, st>>>(rs_coarse, rs_fine, triples, npairs, out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Window descriptors travel host -> device through a page-locked host buffer read by this kernel (zero-copy
 // over PCIe) instead of a cudaMemcpy: the host->device copy engine may be busy for tens of milliseconds with
