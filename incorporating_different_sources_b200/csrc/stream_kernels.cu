@@ -108,6 +108,44 @@ __device__ __forceinline__ void col_accumulate(const double* __restrict__ M, int
     }
 }
 
+// Intraday rows in ONE pass (ld <= 512): per row k the warp holds the whole row in registers, reduces the dot
+// y_k = h_k . w0 with shuffles and accumulates both sum_k h_k and sum_k y_k h_k = H'y.  The centred product the
+// prior needs is H'(y - ybar) = H'y - ybar * (H'1), so the second sweep over the rows (10 GB of DRAM traffic per
+// batch: with ~450 windows in flight the rows do not stay in L2) is not needed.
+__device__ __forceinline__ void hf_single_pass(const double* __restrict__ M, int ld, long long r0, int nr,
+                                               const double* w0s, double* y, double2 (&sum)[NCH], double2 (&wsum)[NCH]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        sum[ch] = make_double2(0.0, 0.0);
+        wsum[ch] = make_double2(0.0, 0.0);
+    }
+    for (int k = warp; k < nr; k += PREP_WARPS) {
+        const double* row = M + (r0 + k) * (long long)ld;
+        double2 x[NCH];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int c = ch * 64 + lane * 2;
+            x[ch] = c < ld ? *reinterpret_cast<const double2*>(row + c) : make_double2(0.0, 0.0);
+        }
+        double dot = 0.0;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int c = ch * 64 + lane * 2;
+            if (c < ld) dot = fma(x[ch].x, w0s[c], fma(x[ch].y, w0s[c + 1], dot));
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) y[k] = dot;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            sum[ch].x += x[ch].x;
+            sum[ch].y += x[ch].y;
+            wsum[ch].x = fma(dot, x[ch].x, wsum[ch].x);
+            wsum[ch].y = fma(dot, x[ch].y, wsum[ch].y);
+        }
+    }
+}
+
 // Cross-warp reduction of the per-lane column partials through shared memory `red`
 // ([PREP_WARPS][512] doubles); thread j of the block ends up owning columns col0+2j, col0+2j+1.
 __device__ __forceinline__ double2 reduce_cols(const double2 (&part)[NCH], double* red) {
@@ -127,7 +165,7 @@ __device__ __forceinline__ double2 reduce_cols(const double2 (&part)[NCH], doubl
     return s;
 }
 
-__global__ void __launch_bounds__(PREP_THREADS, 3) window_prep_kernel(PrepParams p) {
+__global__ void __launch_bounds__(PREP_THREADS, 2) window_prep_kernel(PrepParams p) {
     extern __shared__ double smem[];
     const int K = p.n_window - 1;                 // daily returns per window (F2)
     double* a_s = smem;                           // [K]
@@ -243,13 +281,26 @@ __global__ void __launch_bounds__(PREP_THREADS, 3) window_prep_kernel(PrepParams
     const long long h0 = (long long)p.hf_row0[w];           // first HF return row (first bar dropped, F5)
     const int m = p.hf_m[w];                                // HF returns in the window
     double* y = p.y_ws + (long long)w * p.y_stride;
-    for (int col0 = 0; col0 < p.ldv; col0 += 512) {
-        col_accumulate<true>(p.lr_hf, p.ld, h0, m, col0, nullptr, w0_s, y, col0 > 0, sum, wsum);
-        const double2 hs = reduce_cols(sum, red);
-        const int c = col0 + tid * 2;
+    const bool one_pass = p.ldv <= 512;
+    double2 hs1 = make_double2(0.0, 0.0), q1 = make_double2(0.0, 0.0);
+    if (one_pass) {
+        hf_single_pass(p.lr_hf, p.ld, h0, m, w0_s, y, sum, wsum);
+        hs1 = reduce_cols(sum, red);
+        q1 = reduce_cols(wsum, red);
+        const int c = tid * 2;
         if (c < p.ldv) {
-            double2 hb = make_double2(c < N ? hs.x / (double)m : 0.0, c + 1 < N ? hs.y / (double)m : 0.0);
+            double2 hb = make_double2(c < N ? hs1.x / (double)m : 0.0, c + 1 < N ? hs1.y / (double)m : 0.0);
             *reinterpret_cast<double2*>(p.gvec + (long long)w * p.ldv + c) = hb;
+        }
+    } else {
+        for (int col0 = 0; col0 < p.ldv; col0 += 512) {
+            col_accumulate<true>(p.lr_hf, p.ld, h0, m, col0, nullptr, w0_s, y, col0 > 0, sum, wsum);
+            const double2 hs = reduce_cols(sum, red);
+            const int c = col0 + tid * 2;
+            if (c < p.ldv) {
+                double2 hb = make_double2(c < N ? hs.x / (double)m : 0.0, c + 1 < N ? hs.y / (double)m : 0.0);
+                *reinterpret_cast<double2*>(p.gvec + (long long)w * p.ldv + c) = hb;
+            }
         }
     }
     __syncthreads();
@@ -261,7 +312,7 @@ __global__ void __launch_bounds__(PREP_THREADS, 3) window_prep_kernel(PrepParams
     double yy = 0.0;
     for (int k = tid; k < m; k += PREP_THREADS) {
         const double v = y[k] - ybar;
-        y[k] = v;
+        if (!one_pass) y[k] = v;
         yy = fma(v, v, yy);
     }
     yy = block_sum(yy, scratch);      // block_sum's barriers also publish the centred y to the block
@@ -271,17 +322,30 @@ __global__ void __launch_bounds__(PREP_THREADS, 3) window_prep_kernel(PrepParams
     const double kk = n0 + (double)N + 2.0;
     const double cc = (2.0 * n0) / (kk + sqrt(kk * kk + 4.0 * n0 * v0));   // :415-418
 
-    // ---- HF pass 2: q = H' y_c ;  b = c * S0 w0 + t   (:489)
-    for (int col0 = 0; col0 < p.ldv; col0 += 512) {
-        col_accumulate<false>(p.lr_hf, p.ld, h0, m, col0, y, nullptr, nullptr, false, sum, wsum);
-        const double2 qs = reduce_cols(wsum, red);
-        const int c = col0 + tid * 2;
+    // ---- q = H' y_c ;  b = c * S0 w0 + t   (:489)
+    if (one_pass) {
+        const int c = tid * 2;
         if (c < p.ldv) {
+            const double2 qs = make_double2(fma(-ybar, hs1.x, q1.x), fma(-ybar, hs1.y, q1.y));
             const double2 tv = *reinterpret_cast<const double2*>(p.t + (long long)w * p.ldv + c);
             double2 s0w0 = make_double2(c < N ? alpha * qs.x : 0.0, c + 1 < N ? alpha * qs.y : 0.0);
             double2 bv = make_double2(c < N ? fma(cc, s0w0.x, tv.x) : 0.0, c + 1 < N ? fma(cc, s0w0.y, tv.y) : 0.0);
             *reinterpret_cast<double2*>(p.s0w0 + (long long)w * p.ldv + c) = s0w0;
             *reinterpret_cast<double2*>(p.rhs + (long long)w * p.ldv + c) = bv;
+        }
+    } else {
+        // HF pass 2
+        for (int col0 = 0; col0 < p.ldv; col0 += 512) {
+            col_accumulate<false>(p.lr_hf, p.ld, h0, m, col0, y, nullptr, nullptr, false, sum, wsum);
+            const double2 qs = reduce_cols(wsum, red);
+            const int c = col0 + tid * 2;
+            if (c < p.ldv) {
+                const double2 tv = *reinterpret_cast<const double2*>(p.t + (long long)w * p.ldv + c);
+                double2 s0w0 = make_double2(c < N ? alpha * qs.x : 0.0, c + 1 < N ? alpha * qs.y : 0.0);
+                double2 bv = make_double2(c < N ? fma(cc, s0w0.x, tv.x) : 0.0, c + 1 < N ? fma(cc, s0w0.y, tv.y) : 0.0);
+                *reinterpret_cast<double2*>(p.s0w0 + (long long)w * p.ldv + c) = s0w0;
+                *reinterpret_cast<double2*>(p.rhs + (long long)w * p.ldv + c) = bv;
+            }
         }
     }
     if (tid == 0) {
