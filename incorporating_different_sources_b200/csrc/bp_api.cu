@@ -85,6 +85,9 @@ struct bp_handle {
     size_t pipe_min_bytes = (size_t)256 << 20;
     int n_seg = 0, seg_waited = 0;
     long long lr_hf_done = 0;                  // intraday return rows < lr_hf_done have been computed
+    long long hf_extra_rows = 0;               // rows allocated behind lr_hf for gathered overnight returns
+    int lr_hf_ld_cap = 1;
+    long long lr_hf_rows_cap = 0;              // rows allocated for lr_hf (at the leading dimension it was allocated with)
     long long seg_end[MAX_SEG] = {0};          // return rows < seg_end[s] are valid once ev_seg[s] has fired
     cudaEvent_t ev_seg[MAX_SEG] = {nullptr};
     CUtensorMap map_d, map_hf;
@@ -313,6 +316,8 @@ struct Batch {
     bool band_ok = false;              // consecutive trade dates: the daily pass runs as a banded GEMM
     // intraday block grid (for the pipelined upload): block k of level l ends at return row hf_off + (hf_bmin[l]+k+1)*hf_blk[l]
     int hf_off = 0, hf_bmin[2] = {0, 0}, hf_blk[2] = {0, 0};
+    bool hf_inner = false;             // inner day blocks + gathered overnight rows (see PhasePlan::inner)
+    int hf_nb0 = 0;
 };
 
 // Block grids of one phase, two levels (0 = coarse, 1 = fine; the fine size divides the coarse size): block b of
@@ -321,6 +326,10 @@ struct PhasePlan {
     int blk[2] = {0, 0};
     int off = 0;
     int bmin[2] = {0, 0}, nb[2] = {0, 0};
+    // "inner" blocks (regular intraday calendar): block b is rows off + b*blk + 1 .. off + (b+1)*blk - 1, i.e. a
+    // trading day WITHOUT its first (overnight) return; the overnight rows are gathered into a compact row range
+    // behind the intraday matrix, so a window is [its days' inner blocks] + [one short run of overnight rows]
+    bool inner = false;
 };
 
 inline long long floor_div(long long a, long long b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
@@ -431,6 +440,8 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             if (regular) {
                 plan[0].blk[0] = stride;
                 plan[0].off = b->hf_lo[0] % stride;
+                static const bool no_inner = getenv("BP_NO_INNER_BLOCKS") != nullptr;
+                plan[0].inner = !no_inner && stride >= 8;
             } else if (H0 >= 3 * 64) {
                 plan[0].blk[0] = 64;
                 plan[0].blk[1] = 16;
@@ -440,6 +451,18 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
     auto phase_rows = [&](int ph, int w, int& row0, int& rows) {
         row0 = ph == 0 ? b->hf_lo[w] + 1 : b->day_row[w] - n + 2;
         rows = ph == 0 ? b->hf_hi[w] - b->hf_lo[w] - 1 : n - 1;
+    };
+    // split of window w's rows in phase ph; inner-block plans take every day of the window as a whole block
+    auto split_of = [&](int ph, int w) {
+        int row0, rows;
+        phase_rows(ph, w, row0, rows);
+        if (ph == 0 && plan[0].inner) {
+            Split sp;
+            sp.c_lo = (b->hf_lo[w] - plan[0].off) / plan[0].blk[0];
+            sp.c_hi = sp.c_lo + (b->hf_hi[w] - b->hf_lo[w]) / plan[0].blk[0];
+            return sp;
+        }
+        return split_rows(row0, rows, plan[ph]);
     };
     // phase B (daily rows): the run of whole blocks inside a window is the same for many consecutive windows, so
     // each distinct run [lo, hi) is summed once (range_sum_kernel) and a window adds one tile per run
@@ -453,9 +476,7 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         if (ph == 0 && !need_hf) { plan[ph] = PhasePlan(); continue; }
         long long lo[2] = {1LL << 40, 1LL << 40}, hi[2] = {-(1LL << 40), -(1LL << 40)};
         for (int w = 0; w < W; ++w) {
-            int row0, rows;
-            phase_rows(ph, w, row0, rows);
-            const Split sp = split_rows(row0, rows, plan[ph]);
+            const Split sp = split_of(ph, w);
             if (sp.c_hi > sp.c_lo) { lo[0] = std::min(lo[0], sp.c_lo); hi[0] = std::max(hi[0], sp.c_hi); }
             if (sp.fa_hi > sp.fa_lo) { lo[1] = std::min(lo[1], sp.fa_lo); hi[1] = std::max(hi[1], sp.fa_hi); }
             if (sp.fb_hi > sp.fb_lo) { lo[1] = std::min(lo[1], sp.fb_lo); hi[1] = std::max(hi[1], sp.fb_hi); }
@@ -484,6 +505,19 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
                 CU_TRY(cudaMalloc(&h->store[ph][l], need * sizeof(double)));
                 h->store_cap[ph][l] = need;
             }
+        }
+    }
+    if (plan[0].inner && (plan[0].nb[0] <= 0 || (long long)plan[0].nb[0] > h->hf_extra_rows)) {
+        // no room for the overnight rows behind the intraday matrix (or the reuse was given up): plain day blocks
+        plan[0].inner = false;
+        if (plan[0].blk[0] > 0) {
+            long long lo = 1LL << 40, hi = -(1LL << 40);
+            for (int w = 0; w < W; ++w) {
+                const Split sp = split_of(0, w);
+                if (sp.c_hi > sp.c_lo) { lo = std::min(lo, sp.c_lo); hi = std::max(hi, sp.c_hi); }
+            }
+            if (hi > lo) { plan[0].bmin[0] = (int)lo; plan[0].nb[0] = (int)(hi - lo); }
+            else { plan[0].blk[0] = 0; plan[0].nb[0] = 0; }
         }
     }
     int nranges[2] = {0, 0};
@@ -572,7 +606,13 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             host[(size_t)3 * W + w] = lo + 1;        // first HF return row: the window's first bar has no return (F5)
             host[(size_t)4 * W + w] = m;
             max_m = std::max(max_m, m);
-            write_phase_desc(split_rows(lo + 1, m, plan[0]), plan[0], gd + (size_t)w * GRAM_DESC_INTS);
+            int* dA = gd + (size_t)w * GRAM_DESC_INTS;
+            write_phase_desc(split_of(0, w), plan[0], dA);
+            if (plan[0].inner) {
+                // overnight returns of days 2..last of the window: a run of dA[5]-1 gathered rows behind the matrix
+                dA[0] = (int)(h->R + dA[4] + 1);
+                dA[1] = dA[5] - 1;
+            }
         }
         if (rs) {
             int* dB = gd + (size_t)w * GRAM_DESC_INTS + GRAM_PHASE_INTS;
@@ -609,6 +649,7 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
                 int* d = bd + (size_t)k * GRAM_DESC_INTS + GRAM_PHASE_INTS * ph;
                 d[0] = plan[ph].off + (plan[ph].bmin[l] + k) * plan[ph].blk[l];
                 d[1] = plan[ph].blk[l];
+                if (plan[ph].inner) { d[0] += 1; d[1] -= 1; }
             }
             out->bdesc[ph][l] = plan[ph].nb[l] ? h->desc + (bd - host) : nullptr;
             out->nblocks[ph][l] = plan[ph].nb[l];
@@ -645,6 +686,8 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
     }
     out->hf_off = plan[0].off;
     for (int l = 0; l < 2; ++l) { out->hf_bmin[l] = plan[0].bmin[l]; out->hf_blk[l] = plan[0].blk[l]; }
+    out->hf_inner = plan[0].inner;
+    out->hf_nb0 = plan[0].nb[0];
     out->resampled = rs;
     out->extra_row = rs ? h->desc + 5 * (size_t)W : nullptr;
     out->caps_row = h->desc + 6 * (size_t)W;
@@ -882,6 +925,12 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
 
     const bool any_gram = out->T || out->S0 || out->S1 || solve;
     if (any_gram && !pipelined) {
+        if (mode == BP_MODE_CONJUGATE && B.hf_inner) {
+            launch_gather_strided_rows(h->lr_hf, h->ld, (long long)B.hf_off + (long long)B.hf_bmin[0] * B.hf_blk[0], B.hf_blk[0],
+                                       h->R, 0, B.hf_nb0, h->stream);
+            h->launches++;
+            CU_TRY(cudaGetLastError());
+        }
         if (mode == BP_MODE_CONJUGATE && (out->S0 || out->S1 || solve) && (rc = run_block_precompute(h, B, 0))) return rc;
         if ((out->T || out->S1 || solve) && (rc = run_block_precompute(h, B, 1))) return rc;
     }
@@ -903,6 +952,12 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
                     const long long k = floor_div(r_end - B.hf_off, B.hf_blk[l]) - B.hf_bmin[l];
                     k_ready[l] = (int)std::min<long long>(B.nblocks[0][l], std::max<long long>(k, k_done[l]));
                 }
+            }
+            if (B.hf_inner) {
+                launch_gather_strided_rows(h->lr_hf, h->ld, (long long)B.hf_off + (long long)B.hf_bmin[0] * B.hf_blk[0],
+                                           B.hf_blk[0], h->R, k_done[0], k_ready[0], h->stream);
+                h->launches++;
+                CU_TRY(cudaGetLastError());
             }
             if ((rc = run_block_precompute(h, B, 0, k_done, k_ready))) return rc;
             k_done[0] = k_ready[0];
@@ -1214,7 +1269,9 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
         CU_TRY(cudaMalloc(&h->mcm, sizeof(double) * need_mcm));
         if (need_hf) {
             CU_TRY(cudaMalloc(&h->hf_prices, sizeof(double) * need_hf));
-            CU_TRY(cudaMalloc(&h->lr_hf, sizeof(double) * need_hf));
+            h->lr_hf_ld_cap = ld;
+            h->lr_hf_rows_cap = R + R / 8 + 64;        // + room for the gathered overnight rows
+            CU_TRY(cudaMalloc(&h->lr_hf, sizeof(double) * (size_t)h->lr_hf_rows_cap * ld));
         }
         h->cap_daily = need_daily;
         h->cap_hf = need_hf;
@@ -1271,7 +1328,10 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
     CU_TRY(cudaGetLastError());
     if ((rc = make_map(h, &h->map_d, h->lr_d, D, ld))) return rc;
     if (R > 0) {
-        if ((rc = make_map(h, &h->map_hf, h->lr_hf, R, ld))) return rc;
+        // rows available behind the R return rows at the CURRENT leading dimension
+        h->hf_extra_rows = (long long)((size_t)h->lr_hf_rows_cap * h->lr_hf_ld_cap / ld) - R;
+        if (h->hf_extra_rows < 0) h->hf_extra_rows = 0;
+        if ((rc = make_map(h, &h->map_hf, h->lr_hf, R + h->hf_extra_rows, ld))) return rc;
     } else {
         h->map_hf = h->map_d;
     }

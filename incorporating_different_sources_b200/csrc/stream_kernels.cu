@@ -474,6 +474,23 @@ void launch_range_sum(const double* store, const int* ranges, int n_ranges, int 
     range_sum_kernel<<<grid, 256, 0, st>>>(store, ranges, npairs, out);
 }
 
+// dst row (dst_row0 + k) = src row (src_row0 + k * stride), k in [k0, k1): the overnight returns of the trading
+// days, gathered behind the intraday matrix so that a window reads them as one contiguous run (PhasePlan::inner)
+__global__ void gather_strided_rows_kernel(double* __restrict__ M, int ld, long long src_row0, int stride,
+                                           long long dst_row0, int k0, int k1) {
+    const int k = k0 + blockIdx.x;
+    if (k >= k1) return;
+    const double2* src = reinterpret_cast<const double2*>(M + (src_row0 + (long long)k * stride) * ld);
+    double2* dst = reinterpret_cast<double2*>(M + (dst_row0 + k) * ld);
+    for (int c = threadIdx.x; c < ld / 2; c += blockDim.x) dst[c] = src[c];
+}
+
+void launch_gather_strided_rows(double* M, int ld, long long src_row0, int stride, long long dst_row0, int k0, int k1,
+                                cudaStream_t st) {
+    if (k1 <= k0) return;
+    gather_strided_rows_kernel<<<k1 - k0, 128, 0, st>>>(M, ld, src_row0, stride, dst_row0, k0, k1);
+}
+
 // One tile per distinct RUN TRIPLE (coarse run + fine run on the head side + fine run on the tail side): the three
 // pre-summed run tiles of a window's daily rows are added up once per distinct triple (it changes only when a
 // window edge crosses a fine-block boundary), so a window adds ONE tile per output tile instead of three.
