@@ -934,6 +934,36 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
         if (mode == BP_MODE_CONJUGATE && (out->S0 || out->S1 || solve) && (rc = run_block_precompute(h, B, 0))) return rc;
         if ((out->T || out->S1 || solve) && (rc = run_block_precompute(h, B, 1))) return rc;
     }
+    // Cholesky + solves of the windows [ws, ws+wn) of the workspace
+    auto solve_range = [&](int ws, int wn) -> int {
+        if (wn <= 0) return BP_OK;
+        const Chunk cs = chunk_at(c, L, ws % Wc);
+        SolveParams sp{};
+        sp.n_windows = wn;
+        sp.n_assets = N;
+        sp.ldS = L.ldS;
+        sp.win_stride = L.win_stride;
+        sp.ldv = L.ldv;
+        sp.mode = mode;
+        sp.inv_gamma = 1.0 / b->risk_aversion;         // the reference evaluates (1/gamma) * nu (:836,:849)
+        sp.S = cs.S;
+        sp.rhs = cs.rhs;
+        sp.scal = cs.scal;
+        sp.w1 = cs.w1;
+        sp.nu = cs.nu;
+        sp.weights = cs.weights;
+        sp.status = cs.status;
+        CUtensorMap smap;
+        int rcs = make_solve_map(h, &smap, cs.S, (long long)wn * L.rowsS, L.ldS);
+        if (rcs) return rcs;
+        {
+            StageTimer tm(h, BP_STAGE_SOLVE);
+            CU_TRY(launch_chol_solve(sp, smap, h->sm_count, h->stream));
+        }
+        h->launches++;
+        return BP_OK;
+    };
+    int w_solved = 0;          // windows already solved by the pipelined path (full waves, between the upload segments)
     if (pipelined) {
         if ((rc = run_block_precompute(h, B, 1))) return rc;          // daily blocks do not wait for the bars
         int w_done = 0, k_done[2] = {0, 0};
@@ -977,6 +1007,18 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
                 if ((rc = run_gram(h, gram_params(h, B, L, cw, w_done, w_end - w_done, GRAM_S1), B.resampled))) return rc;
                 w_done = w_end;
             }
+            // Solve the full waves of windows that are ready: the compute stream would otherwise idle until the next
+            // segment arrives (the copy takes longer than the statistics / Gram stages), and after the last segment
+            // only the remainder (less than one wave) is left instead of every window.  Full waves cost nothing in
+            // occupancy whichever of the copy and the GPU is the bottleneck.
+            if (!last) {
+                const int wave = chol_wave_windows(h->sm_count);
+                const int wn = (w_done - w_solved) / wave * wave;
+                if (wn > 0) {
+                    if ((rc = solve_range(w_solved, wn))) return rc;
+                    w_solved += wn;
+                }
+            }
         }
         h->seg_waited = h->n_seg;
         h->hf_pending = false;
@@ -1014,28 +1056,7 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
             if (rc) return rc;
         }
         if (solve) {
-            SolveParams sp{};
-            sp.n_windows = wc;
-            sp.n_assets = N;
-            sp.ldS = L.ldS;
-            sp.win_stride = L.win_stride;
-            sp.ldv = L.ldv;
-            sp.mode = mode;
-            sp.inv_gamma = 1.0 / b->risk_aversion;         // the reference evaluates (1/gamma) * nu (:836,:849)
-            sp.S = c.S;
-            sp.rhs = c.rhs;
-            sp.scal = c.scal;
-            sp.w1 = c.w1;
-            sp.nu = c.nu;
-            sp.weights = c.weights;
-            sp.status = c.status;
-            CUtensorMap smap;
-            if ((rc = make_solve_map(h, &smap, c.S, (long long)wc * L.rowsS, L.ldS))) return rc;
-            {
-                StageTimer tm(h, BP_STAGE_SOLVE);
-                CU_TRY(launch_chol_solve(sp, smap, h->sm_count, h->stream));
-            }
-            h->launches++;
+            if ((rc = solve_range(w0 + w_solved, wc - w_solved))) return rc;
             if ((rc = emit_vec(h, c.weights, L, wc, out->weights ? out->weights + ov : nullptr))) return rc;
             if ((rc = emit_vec(h, c.nu, L, wc, out->nu ? out->nu + ov : nullptr))) return rc;
             if ((rc = emit_vec(h, c.w1, L, wc, out->w1 ? out->w1 + ov : nullptr))) return rc;

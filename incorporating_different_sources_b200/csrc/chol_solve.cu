@@ -443,6 +443,16 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
 #undef PROF
 }
 
+// windows the solver works on concurrently (one CTA each): a launch of a multiple of this runs full waves
+int chol_wave_windows(int sm_count) {
+    static const int ctas_per_sm = [] {
+        const char* e = getenv("BP_CHOL_CTAS_PER_SM");      // tuning knob (default: CH_OCC)
+        const int v = e ? atoi(e) : CH_OCC;
+        return v >= 1 && v <= CH_OCC ? v : CH_OCC;
+    }();
+    return ctas_per_sm * sm_count;
+}
+
 size_t chol_smem_bytes(int n_assets) {
     const int Nr = (n_assets + NB - 1) / NB * NB;
     // xs aliases the stage ring: it must hold it
@@ -456,12 +466,7 @@ cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int
     if (smem == 0) return cudaErrorInvalidValue;      // N too large for the aliased back-substitution vector
     cudaError_t e = cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    static const int ctas_per_sm = [] {
-        const char* e = getenv("BP_CHOL_CTAS_PER_SM");      // tuning knob (default: CH_OCC)
-        const int v = e ? atoi(e) : CH_OCC;
-        return v >= 1 && v <= CH_OCC ? v : CH_OCC;
-    }();
-    int grid = ctas_per_sm * sm_count;
+    int grid = chol_wave_windows(sm_count);
     if (grid > p.n_windows) grid = p.n_windows;
     static const bool profile = getenv("BP_CHOL_PROFILE") != nullptr;
     if (profile) {

@@ -175,5 +175,6 @@ constexpr int GRAM_TILE = 128;     // output tile edge
 cudaError_t launch_gram(const GramParams& p, const CUtensorMap& map0, const CUtensorMap& map1, int sm_count,
                         cudaStream_t st);
 cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int sm_count, cudaStream_t st);
+int chol_wave_windows(int sm_count);
 
 }  // namespace bp

@@ -197,19 +197,21 @@ def test_gpu_async_upload_matches_blocking(engine):
         engine.synchronize()
         assert np.array_equal(got, ref)
 
-@pytest.mark.parametrize("segments,order", [(2, "sorted"), (5, "sorted"), (8, "sorted"), (8, "shuffled")])
-def test_gpu_pipelined_upload_matches_blocking(engine, segments, order):
+@pytest.mark.parametrize("segments,order,n_days", [(2, "sorted", 200), (5, "sorted", 200), (8, "sorted", 200),
+                                                   (8, "shuffled", 200), (8, "sorted", 1100)])
+def test_gpu_pipelined_upload_matches_blocking(engine, segments, order, n_days):
     """Segmented asynchronous intraday upload: the conjugate statistics / Gram stages of the windows whose bars
     have arrived run while later segments are still being copied.  Same kernels, same descriptors: bit-identical
     to the blocking upload, for date-sorted batches (one chunk of windows per segment) and for shuffled ones
-    (everything waits for the last segment)."""
+    (everything waits for the last segment).  The 1,100-day case has more windows than the solver works on at a
+    time (6 per SM), so the full waves that are ready are solved between the segments."""
     import torch
     from incorporating_different_sources_b200.synthetic import generate_market
     from incorporating_different_sources_b200.windows import ffill_rows, plan_daily_windows
-    mkt = generate_market(40, 200, seed=23)
+    mkt = generate_market(40, n_days, seed=23)
     spec = dict(weighting_strategy="conjugate_hf_vix_vw", size=40, risk_aversion=5, rolling_window=60,
                 rolling_window_frequency="daily", mcm_scaling=1)
-    d_idx = list(range(60, 200))
+    d_idx = list(range(60, n_days))
     if order == "shuffled":
         d_idx = list(np.random.default_rng(3).permutation(d_idx))
     arrays = dict(prices=mkt.prices, caps=mkt.caps, hf_prices=mkt.hf_prices, mcm=np.stack([mkt.vix, mkt.epu]),

@@ -37,3 +37,11 @@ for _ in range(2):
     torch.cuda.synchronize(); t0 = time.perf_counter(); x.copy_(src, non_blocking=True); torch.cuda.synchronize()
     dt = time.perf_counter() - t0
 print(f"pinned H2D {src.numel()*8/1e9:.2f} GB in {1e3*dt:.1f} ms = {src.numel()*8/1e9/dt:.1f} GB/s")
+# stage launches / device time of one more end-to-end iteration (shows whether the pipelined path split the solve)
+eng.set_stage_timing(True); eng.stage_times()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+eng.upload_market(**host, async_copy=True)
+eng.jeffreys(jb, outputs=("weights", "status"), into={"weights": hw_jv, "status": hs_j})
+eng.conjugate(cb, outputs=("weights", "status"), into={"weights": hw_cv, "status": hs_c})
+eng.synchronize(); t1 = time.perf_counter()
+print(f"timed iteration {1e3*(t1-t0):.1f} ms; stages:", eng.stage_times())
