@@ -105,3 +105,33 @@ def test_config4_independent_paths(engine):
         assert relerr(got["weights"], ref) <= TOL
         outs.append(got["weights"])
     assert not np.allclose(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("n_windows", [3, 40])
+def test_wide_universe_beyond_512_columns(engine, n_windows):
+    """N = 520 (> 512 columns: two column passes in the streaming prep, 5 x 5 Gram tiles, 17 Cholesky panels),
+    conjugate with a 7-day intraday look-back and Jeffreys with n = 640, single windows and a batch of consecutive
+    dates (block reuse, banded-GEMM prep, inner day blocks)."""
+    from incorporating_different_sources_b200.engine import upload_synthetic
+    from incorporating_different_sources_b200.synthetic import generate_market
+    from incorporating_different_sources_b200.windows import plan_daily_windows
+    n = 520
+    mkt = generate_market(n, 700, seed=41)
+    upload_synthetic(engine, mkt)
+    d_idx = list(range(700 - n_windows, 700))
+    cols = np.arange(n)
+    check = d_idx if n_windows <= 3 else [d_idx[0], d_idx[17], d_idx[-1]]
+    cspec = _spec("conjugate_hf_vix_vw", n, rolling_window=252)
+    cb = plan_daily_windows(cspec, mkt.dates, d_idx, mkt.hf_ts, hf_lookback_days=7)
+    got = engine.conjugate(cb, outputs=("weights", "scalars", "status"))
+    assert not got["status"].any()
+    for d in check:
+        ref = bo.conjugate_window(cspec, mkt, d, cols, hf_lookback_days=7)
+        assert relerr(got["weights"][d_idx.index(d)], ref["weights"]) <= TOL
+    jspec = _spec("jeffreys", n, rolling_window=640)
+    jb = plan_daily_windows(jspec, mkt.dates, d_idx, need_hf=False)
+    gotj = engine.jeffreys(jb, outputs=("weights", "status"))
+    assert not gotj["status"].any()
+    for d in check:
+        ref = bo.jeffreys_window(jspec, mkt, d, cols)
+        assert relerr(gotj["weights"][d_idx.index(d)], ref["weights"]) <= TOL
