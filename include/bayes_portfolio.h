@@ -179,6 +179,32 @@ int bp_conjugate_batched(bp_handle* h, const bp_window_batch* b, const bp_output
 /* calculate_jeffreys_portfolio (:838-849) for W windows. */
 int bp_jeffreys_batched(bp_handle* h, const bp_window_batch* b, const bp_outputs* out);
 
+/* Sibling estimators on the sample moments of the same daily window; they share the
+ * batched Gram and the batched Cholesky kernels of the Bayesian path.
+ *  BP_ESTIMATOR_JORION     calculate_jorion_portfolio (:851-895): Bayes-Stein shrinkage of the sample mean towards
+ *                          the grand mean mu_g and the matching predictive covariance V_PJ; ONE factorisation of the
+ *                          centred Gram with two right-hand sides (t and 1), V_PJ^-1 by Sherman-Morrison.
+ *                          Needs rolling_window - 1 > N + 2 (:879).  scalars: BP_SCAL_JORION_*.
+ *  BP_ESTIMATOR_SHRINKAGE  calculate_shrinkage_portfolio (:703-758) in the closed form of the reference's own CHECK
+ *                          (:748-756): weights = (1/gamma) Sigma_LW^-1 mu_hat with the Ledoit-Wolf covariance of
+ *                          pypfopt's CovarianceShrinkage.ledoit_wolf() (= sklearn.covariance.ledoit_wolf).  The
+ *                          reference returns these weights after a cvxpy solve and clean_weights() rounding; the
+ *                          rounding is the Python shim's job.  scalars: BP_SCAL_LW_*.
+ * Outputs honoured: weights, nu (weights before 1/gamma), w1 (C^-1 t), t, rhs, scalars, status, S1 (Jorion: the
+ * centred Gram C = (m-1) V_hat; shrinkage: m Sigma_LW), m = rolling_window - 1. */
+#define BP_ESTIMATOR_JORION 1
+#define BP_ESTIMATOR_SHRINKAGE 2
+#define BP_SCAL_JORION_MU_G 0          /* grand mean                                  :882               */
+#define BP_SCAL_JORION_LAMBDA 1        /* lambda_hat                                  :885               */
+#define BP_SCAL_JORION_V 2             /* v_hat                                       :887               */
+#define BP_SCAL_JORION_Q 4             /* (mu_hat - mu_g 1)' V_bar^-1 (mu_hat - mu_g 1)                  */
+#define BP_SCAL_JORION_ONE_VINV_ONE 5  /* 1' V_bar^-1 1                                                  */
+#define BP_SCAL_LW_SHRINKAGE 0         /* Ledoit-Wolf shrinkage intensity                                */
+#define BP_SCAL_LW_MU 1                /* trace(emp_cov) / N                                             */
+#define BP_SCAL_LW_BETA 2
+#define BP_SCAL_LW_DELTA 4
+int bp_estimator_batched(bp_handle* h, const bp_window_batch* b, int estimator, const bp_outputs* out);
+
 /* The posterior MOMENTS of W windows without the solve: any of t, w0, rhs, scalars (n0, n1, c, v0, MCM
  * average), T, S0, S1 (mode 0: conjugate S1 = S0 + T, :335-358; mode 1: Jeffreys T - tt'/n, :600-601).
  * Backs calculate_average_mcm_window / calculate_conjugate_prior_n / _posterior_n / _prior_w /

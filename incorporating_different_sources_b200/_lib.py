@@ -13,6 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbayes_portfolio.so")
 
 BP_NSCAL = 12
+EST_JORION, EST_SHRINKAGE = 1, 2
+SCAL_JORION = dict(mu_g=0, lambda_hat=1, v_hat=2, q=4, one_vinv_one=5)
+SCAL_LW = dict(shrinkage=0, mu=1, beta=2, delta=4)
 SCAL = dict(n0=0, n1=1, alpha=2, beta=3, c=4, v0=5, m=6, sum_a=7, v1=8, mcm_avg=9)
 
 BP_OK, BP_ERR_INVALID, BP_ERR_CUDA, BP_ERR_NO_DEVICE, BP_ERR_STATE = 0, 1, 2, 3, 4
@@ -24,7 +27,7 @@ EXPORTED = [
     "bp_jeffreys_batched", "bp_set_stage_timing", "bp_get_stage_times",
     "bp_excess_returns", "bp_quadratic_form", "bp_dense_posterior", "bp_moments_batched",
     "bp_upload_market_async", "bp_backtest_batched", "bp_get_gram_work", "bp_set_reuse_min_windows", "bp_set_upload_pipeline", "bp_set_async_outputs",
-    "bp_set_resampled",
+    "bp_set_resampled", "bp_estimator_batched",
 ]
 BP_NSTAGE = 8
 STAGES = ("logret", "prep", "gram", "solve")
@@ -119,6 +122,7 @@ def load():
     lib.bp_set_stage_timing.argtypes = [C.c_void_p, C.c_int]
     lib.bp_get_stage_times.argtypes = [C.c_void_p, c_double_p, C.POINTER(C.c_longlong)]
     lib.bp_moments_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.c_int, C.POINTER(Outputs)]
+    lib.bp_estimator_batched.argtypes = [C.c_void_p, C.POINTER(WindowBatchDesc), C.c_int, C.POINTER(Outputs)]
     lib.bp_set_resampled.argtypes = [C.c_void_p, C.POINTER(ResampledDesc)]
     lib.bp_get_gram_work.argtypes = [C.c_void_p, c_double_p]
     lib.bp_set_reuse_min_windows.argtypes = [C.c_void_p, C.c_int]

@@ -126,7 +126,11 @@ def calculate_portfolio_weights(trading_date_ts, portfolio_spec, market_data):
                                                        epu.loc[epu.index <= trading_date_ts], rf)
     if strat == "jeffreys":
         return pc.calculate_jeffreys_portfolio(portfolio_spec, trading_date_ts, prices, rf)
-    if strat in ("shrinkage", "black_litterman", "jorion", "greyserman"):
+    if strat == "jorion":
+        return pc.calculate_jorion_portfolio(portfolio_spec, trading_date_ts, prices, rf)
+    if strat == "shrinkage":
+        return pc.calculate_shrinkage_portfolio(portfolio_spec, trading_date_ts, prices, rf)
+    if strat in ("black_litterman", "greyserman"):
         raise NotImplementedError(f"strategy {strat!r} is out of scope of the CUDA path (SURVEY §2)")
     raise ValueError("Unknown weights spec.")                                                     # :1050
 
@@ -134,6 +138,7 @@ def calculate_portfolio_weights(trading_date_ts, portfolio_spec, market_data):
 def _batched_weights(engine, portfolio_spec, market_data, dates_all, reb_pos, universes):
     """Weights [R][N_all] (0 outside each date's universe) for every rebalance date, one upload + one batched
     call per distinct asset set."""
+    from . import portfolio_calculations as pc
     prices_df = market_data["stock_prices_df"]
     caps_df = market_data["stock_market_caps_df"]
     intr_df = market_data["stock_intraday_prices_df"]
@@ -182,15 +187,18 @@ def _batched_weights(engine, portfolio_spec, market_data, dates_all, reb_pos, un
             res = engine.conjugate(batch, outputs=("weights", "status"))
             _raise_on_status(res["status"], dates_all, d_idx)
             w = res["weights"]
-        elif strat == "jeffreys":
+        elif strat in ("jeffreys", "jorion", "shrinkage"):
             if weekly:
                 rows_w, batch = plan_weekly_windows(portfolio_spec, dates_ns, d_idx, rf_dates, rf_vals, None, need_hf=False)
                 engine.set_resampled(rows_w)
             else:
                 batch = plan_daily_windows(portfolio_spec, dates_ns, d_idx, need_hf=False)
-            res = engine.jeffreys(batch, outputs=("weights", "status"))
+            run = {"jeffreys": engine.jeffreys, "jorion": engine.jorion, "shrinkage": engine.shrinkage}[strat]
+            res = run(batch, outputs=("weights", "status"))
             _raise_on_status(res["status"], dates_all, d_idx)
             w = res["weights"]
+            if strat == "shrinkage":
+                w = pc.clean_weights(w)                        # the reference returns clean_weights() (:743)
         else:
             raise ValueError("Unknown weights spec.")
         for k, r in enumerate(rows):

@@ -890,7 +890,7 @@ int finish(bp_handle* h) {
 }
 
 // shared driver of bp_conjugate_batched / bp_jeffreys_batched / bp_stats_batched / bp_hf_cov_batched
-int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, int mode, bool solve) {
+int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, int mode, bool solve, int estimator = BP_EST_NONE) {
     Batch B;
     int rc = upload_batch(h, b, mode == BP_MODE_CONJUGATE, &B);
     if (rc) return rc;
@@ -920,8 +920,10 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
             h->band_stats_cap = need_st;
         }
     }
-    if (solve && mode == BP_MODE_CONJUGATE && !(b->risk_aversion != 0.0))
+    if (solve && (mode == BP_MODE_CONJUGATE || estimator != BP_EST_NONE) && !(b->risk_aversion != 0.0))
         return fail(BP_ERR_INVALID, "risk_aversion must be non-zero");
+    if (estimator == BP_EST_JORION && B.n - 1 - N - 2 <= 0)
+        return fail(BP_ERR_INVALID, "Jorion needs T - N - 2 > 0 (T = rolling_window - 1 returns, :879)");
 
     const bool any_gram = out->T || out->S0 || out->S1 || solve;
     if (any_gram && !pipelined) {
@@ -945,6 +947,8 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
         sp.win_stride = L.win_stride;
         sp.ldv = L.ldv;
         sp.mode = mode;
+        sp.estimator = estimator;
+        sp.n_returns = B.n - 1;
         sp.inv_gamma = 1.0 / b->risk_aversion;         // the reference evaluates (1/gamma) * nu (:836,:849)
         sp.S = cs.S;
         sp.rhs = cs.rhs;
@@ -1028,6 +1032,7 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
         const size_t ov = (size_t)w0 * N, om = (size_t)w0 * N * N;
         if (!pipelined) {
             PrepParams pp = prep_params(h, b, B, L, c, w0, mode);
+            if (estimator != BP_EST_NONE) pp.beta_den = B.n - 1;       // sample covariance: centre with 1/m, m = n-1 returns
             {
                 StageTimer tm(h, BP_STAGE_PREP);
                 CU_TRY(launch_window_prep(pp, wc, h->stream, h->D));
@@ -1051,6 +1056,28 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
             if (!pipelined) {
                 rc = run_gram(h, gram_params(h, B, L, c, w0, wc, mode == BP_MODE_CONJUGATE ? GRAM_S1 : GRAM_J), B.resampled);
                 if (rc) return rc;
+            }
+            if (estimator == BP_EST_SHRINKAGE) {
+                // C = X_c'X_c  ->  m Sigma_LW = (1 - shrinkage) C + shrinkage mu m I, in place (:727-729)
+                ShrinkParams q{};
+                q.n_windows = wc;
+                q.n_assets = N;
+                q.n_window = B.n;
+                q.ld = h->ld;
+                q.ldv = L.ldv;
+                q.ldS = L.ldS;
+                q.win_stride = L.win_stride;
+                q.lr_daily = B.resampled ? h->lr_w : h->lr_d;
+                q.rf_row = B.resampled ? h->rf_w : h->rf_row;
+                q.day_row = B.day_row + w0;
+                q.extra_row = B.extra_row ? B.extra_row + w0 : nullptr;
+                q.span_days = B.span + w0;
+                q.t = c.t;
+                q.S = c.S;
+                q.scal = c.scal;
+                StageTimer tm(h, BP_STAGE_PREP);
+                CU_TRY(launch_lw_shrink(q, h->stream));
+                h->launches++;
             }
             rc = emit_sym(h, c.S, L, wc, out->S1 ? out->S1 + om : nullptr);
             if (rc) return rc;
@@ -1408,6 +1435,14 @@ int bp_conjugate_batched(bp_handle* h, const bp_window_batch* b, const bp_output
 int bp_jeffreys_batched(bp_handle* h, const bp_window_batch* b, const bp_outputs* out) {
     if (!out) return fail(BP_ERR_INVALID, "outputs missing");
     return run_batches(h, b, out, BP_MODE_JEFFREYS, true);
+}
+
+int bp_estimator_batched(bp_handle* h, const bp_window_batch* b, int estimator, const bp_outputs* out) {
+    if (!h || !b || !out) return fail(BP_ERR_INVALID, "null argument");
+    if (estimator != BP_EST_JORION && estimator != BP_EST_SHRINKAGE)
+        return fail(BP_ERR_INVALID, "estimator must be BP_ESTIMATOR_JORION or BP_ESTIMATOR_SHRINKAGE");
+    if (out->T || out->S0) return fail(BP_ERR_INVALID, "estimator batches do not return T / S0 (use bp_stats_batched)");
+    return run_batches(h, b, out, BP_MODE_JEFFREYS, true, estimator);
 }
 
 int bp_stats_batched(bp_handle* h, const bp_window_batch* b, double* t, double* T) {

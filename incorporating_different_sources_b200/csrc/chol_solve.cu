@@ -134,7 +134,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
 // generic-proxy global writes (the factor) must be visible to later async-proxy (TMA) reads
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-__global__ void __launch_bounds__(CH_THREADS, CH_OCC)
+// NRHS = 1: the posterior solves of the conjugate / Jeffreys path.  NRHS = 2 (Jorion, :851-895): a second
+// right-hand side (the vector of ones) rides along as row Nr+1, so that both C^-1 t and C^-1 1 come out of ONE
+// factorisation; the Bayes-Stein combination is the epilogue of this kernel.
+template <int NRHS>
+__global__ void __launch_bounds__(CH_THREADS, NRHS == 1 ? CH_OCC : 4)
 chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p) {
     extern __shared__ unsigned char sm_raw[];
     __shared__ uint64_t full_bar[CH_STAGES];
@@ -143,10 +147,10 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
     // 1024-byte alignment by pointer arithmetic on the shared array (keeps the shared address space)
     unsigned char* stage_mem = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
     double* P = reinterpret_cast<double*>(stage_mem + CH_STAGES * CH_STAGE_BYTES);   // [32][LDQ]: L_d (lower) + inv(L_d)' (upper)
-    double* red = P + NB * LDQ;            // [CH_WARPS][32]
-    double* scratch = red + CH_WARPS * NB; // [40]
-    // solution vector of the back substitution: aliases the TMA stages (after the last panel they are idle)
-    double* xs = reinterpret_cast<double*>(stage_mem);   // [Nr]
+    double* red = P + NB * LDQ;            // [NRHS][CH_WARPS][32]
+    double* scratch = red + NRHS * CH_WARPS * NB; // [40]
+    // solution vectors of the back substitution: alias the TMA stages (after the last panel they are idle)
+    double* xs = reinterpret_cast<double*>(stage_mem);   // [NRHS][Nr]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tig = lane & 3;
@@ -187,6 +191,8 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
         const int grow0 = w * rowsS;           // first row of this window in the tensor map
         if (tid == 0) fail_s = 0;
         for (int j = tid; j < ld; j += CH_THREADS) S[(long long)Nr * ld + j] = j < N ? rhs[j] : 0.0;
+        if constexpr (NRHS == 2)
+            for (int j = tid; j < ld; j += CH_THREADS) S[(long long)(Nr + 1) * ld + j] = j < N ? 1.0 : 0.0;
         fence_proxy_async_all();
         __syncthreads();
 
@@ -220,7 +226,7 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
 #pragma unroll
                 for (int i = 0; i < TPW; ++i) {
                     const int row = j0 + 8 * (slab0 + warp + CH_WARPS * i) + g;
-                    const bool real = i < ni && (row < N || row == Nr);
+                    const bool real = i < ni && (row < N || (row >= Nr && row < Nr + NRHS));
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt) {
                         const int col = j0 + 8 * nt + 2 * tig;
@@ -268,7 +274,7 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
 #pragma unroll
                     for (int i = 0; i < TPW; ++i) {
                         const int row = j0 + 8 * (slab0 + warp + CH_WARPS * i) + g;
-                        const bool real = row < N || row == Nr;
+                        const bool real = row < N || (row >= Nr && row < Nr + NRHS);
 #pragma unroll
                         for (int nt = 0; nt < 4; ++nt) {
                             const int col = j0 + 8 * nt + 2 * tig;
@@ -343,7 +349,7 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
                     const int q = slab0 + warp + CH_WARPS * i;     // m-tile index within the panel
                     if (i >= ni || q < NB / 8) continue;
                     const int row = j0 + 8 * q + g;
-                    const bool real = row < N || row == Nr;
+                    const bool real = row < N || (row >= Nr && row < Nr + NRHS);
 #pragma unroll
                     for (int cb = 0; cb < NB / 8; ++cb) {
                         double x0 = 0.0, x1 = 0.0;
@@ -366,32 +372,43 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
             PROF(2)
         }
 
-        // ---------------- z = L^-1 b sits in row Nr;  v1 = z'z = w1' S1 w1   (:574)
+        // ---------------- z = L^-1 b sits in row Nr (+r);  v1 = z'z = w1' S1 w1   (:574)
         double zz = 0.0;
         for (int j = tid; j < Nr; j += CH_THREADS) {
             const double z = j < N ? S[(long long)Nr * ld + j] : 0.0;
             xs[j] = z;
             zz = fma(z, z, zz);
+            if constexpr (NRHS == 2) xs[Nr + j] = j < N ? S[(long long)(Nr + 1) * ld + j] : 0.0;
         }
         const double v1 = block_sum(zz, scratch);
 
-        // ---------------- back substitution  L' x = z, panels in reverse
+        // ---------------- back substitution  L' x = z, panels in reverse (warp r finishes right-hand side r)
         for (int j0 = Nr - NB; j0 >= 0; j0 -= NB) {
-            double part = 0.0;
+            double part[NRHS];
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) part[r] = 0.0;
             const int col = j0 + lane;
             if (col < N) {
                 int i = j0 + NB + warp;
                 for (; i + 3 * CH_WARPS < N; i += 4 * CH_WARPS) {        // 4 independent loads in flight
                     const double s0 = S[(long long)i * ld + col], s1 = S[(long long)(i + CH_WARPS) * ld + col];
                     const double s2 = S[(long long)(i + 2 * CH_WARPS) * ld + col], s3 = S[(long long)(i + 3 * CH_WARPS) * ld + col];
-                    part = fma(s0, xs[i], part);
-                    part = fma(s1, xs[i + CH_WARPS], part);
-                    part = fma(s2, xs[i + 2 * CH_WARPS], part);
-                    part = fma(s3, xs[i + 3 * CH_WARPS], part);
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) {
+                        part[r] = fma(s0, xs[r * Nr + i], part[r]);
+                        part[r] = fma(s1, xs[r * Nr + i + CH_WARPS], part[r]);
+                        part[r] = fma(s2, xs[r * Nr + i + 2 * CH_WARPS], part[r]);
+                        part[r] = fma(s3, xs[r * Nr + i + 3 * CH_WARPS], part[r]);
+                    }
                 }
-                for (; i < N; i += CH_WARPS) part = fma(S[(long long)i * ld + col], xs[i], part);
+                for (; i < N; i += CH_WARPS) {
+                    const double sv = S[(long long)i * ld + col];
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) part[r] = fma(sv, xs[r * Nr + i], part[r]);
+                }
             }
-            red[warp * NB + lane] = part;
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) red[(r * CH_WARPS + warp) * NB + lane] = part[r];
             for (int i = warp; i < NB; i += CH_WARPS) {
                 const int row = j0 + i;
                 double v;
@@ -400,10 +417,11 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
                 P[i * LDQ + lane] = v;
             }
             __syncthreads();
-            if (warp == 0) {
-                double r = xs[col];
+            if (warp < NRHS) {
+                double* xr = xs + warp * Nr;
+                double r = xr[col];
 #pragma unroll
-                for (int wv = 0; wv < CH_WARPS; ++wv) r -= red[wv * NB + lane];
+                for (int wv = 0; wv < CH_WARPS; ++wv) r -= red[(warp * CH_WARPS + wv) * NB + lane];
                 const double rd = 1.0 / P[lane * LDQ + lane];      // all 32 reciprocals in parallel
 #pragma unroll
                 for (int k = NB - 1; k >= 0; --k) {
@@ -411,7 +429,7 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
                     if (lane == k) r = xk;
                     if (lane < k) r = fma(-P[k * LDQ + lane], xk, r);
                 }
-                xs[col] = r;
+                xr[col] = r;
             }
             __syncthreads();
         }
@@ -419,6 +437,57 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
         PROF(3)
         // ---------------- posterior scalars and weights
         double* scal = p.scal + (long long)w * BP_S_COUNT;
+        if constexpr (NRHS == 2) {
+            // Jorion's Bayes-Stein estimator (:851-895) from y = C^-1 t and z = C^-1 1, C = (m-1) V_hat the centred
+            // Gram of the m excess returns:  V_bar = kappa C, kappa = m / ((m-N-2)(m-1))  (:876-879);
+            //   mu_g = 1'V_bar^-1 mu_hat / 1'V_bar^-1 1 (:882), q = (mu_hat - mu_g 1)' V_bar^-1 (mu_hat - mu_g 1),
+            //   lambda = (N+2)/q (:885), v = (N+2)/((N+2) + m q) (:887),
+            //   V_PJ = a V_bar + b 11', a = 1 + 1/(m+lambda), b = lambda / (m (m+1+lambda) 1'V_bar^-1 1) (:888),
+            //   mu_PJ = (1-v) mu_hat + v mu_g 1 (:889), weights = (1/gamma) V_PJ^-1 mu_PJ (:891-893) by Sherman-Morrison.
+            const double* y = xs;
+            const double* z = xs + Nr;
+            double sy = 0.0, sz = 0.0, ty = 0.0;
+            for (int j = tid; j < N; j += CH_THREADS) {
+                sy += y[j];
+                sz += z[j];
+                ty = fma(rhs[j], y[j], ty);
+            }
+            sy = block_sum(sy, scratch);
+            sz = block_sum(sz, scratch);
+            ty = block_sum(ty, scratch);
+            const double m = (double)p.n_returns, Nd = (double)N;
+            const double kappa = m / ((m - Nd - 2.0) * (m - 1.0));
+            const double sym = sy / m;                               // 1'C^-1 mu_hat
+            const double mu_g = sym / sz;
+            const double q = (ty / (m * m) - sym * sym / sz) / kappa;
+            const double lambda = (Nd + 2.0) / q;
+            const double v = (Nd + 2.0) / ((Nd + 2.0) + m * q);
+            const double a = 1.0 + 1.0 / (m + lambda);
+            const double one_vinv_one = sz / kappa;
+            const double b = lambda / (m * (m + 1.0 + lambda)) / one_vinv_one;
+            const double iak = 1.0 / (a * kappa);
+            const double one_r = sym * iak;                          // 1'(aV_bar)^-1 mu_PJ  (since mu_g 1'z = 1'y/m)
+            const double one_s = sz * iak;                           // 1'(aV_bar)^-1 1
+            const double corr = b * one_r / (1.0 + b * one_s);
+            for (int j = tid; j < p.ldv; j += CH_THREADS) {
+                double yj = 0.0, nu = 0.0;
+                if (j < N) {
+                    yj = y[j];
+                    const double rj = ((1.0 - v) * (yj / m) + v * mu_g * z[j]) * iak;
+                    nu = rj - corr * (z[j] * iak);
+                }
+                p.w1[(long long)w * p.ldv + j] = yj;
+                p.nu[(long long)w * p.ldv + j] = nu;
+                p.weights[(long long)w * p.ldv + j] = p.inv_gamma * nu;
+            }
+            if (tid == 0) {
+                scal[BP_S_JORION_MU_G] = mu_g;
+                scal[BP_S_JORION_LAMBDA] = lambda;
+                scal[BP_S_JORION_V] = v;
+                scal[BP_S_JORION_Q] = q;
+                scal[BP_S_JORION_ONE_VINV_ONE] = one_vinv_one;
+            }
+        } else {
         double mult = 1.0;
         if (p.mode == BP_MODE_CONJUGATE) {
             const double n1 = scal[BP_S_N1];
@@ -430,6 +499,7 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
             p.w1[(long long)w * p.ldv + j] = wv;
             p.nu[(long long)w * p.ldv + j] = nu;
             p.weights[(long long)w * p.ldv + j] = p.inv_gamma * nu;
+        }
         }
         if (tid == 0) {
             scal[BP_S_V1] = v1;
@@ -453,21 +523,27 @@ int chol_wave_windows(int sm_count) {
     return ctas_per_sm * sm_count;
 }
 
-size_t chol_smem_bytes(int n_assets) {
+size_t chol_smem_bytes(int n_assets, int nrhs) {
     const int Nr = (n_assets + NB - 1) / NB * NB;
     // xs aliases the stage ring: it must hold it
-    if ((size_t)CH_STAGES * CH_STAGE_BYTES < sizeof(double) * (size_t)Nr) return 0;
-    return (size_t)CH_TMA_SMEM + sizeof(double) * (size_t)(NB * LDQ + CH_WARPS * NB + 40);
+    if ((size_t)CH_STAGES * CH_STAGE_BYTES < sizeof(double) * (size_t)Nr * nrhs) return 0;
+    return (size_t)CH_TMA_SMEM + sizeof(double) * (size_t)(NB * LDQ + nrhs * CH_WARPS * NB + 40);
 }
 
 cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int sm_count, cudaStream_t st) {
     if (p.n_windows <= 0) return cudaSuccess;
-    const size_t smem = chol_smem_bytes(p.n_assets);
+    const int nrhs = p.estimator == BP_EST_JORION ? 2 : 1;
+    const size_t smem = chol_smem_bytes(p.n_assets, nrhs);
     if (smem == 0) return cudaErrorInvalidValue;      // N too large for the aliased back-substitution vector
-    cudaError_t e = cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = nrhs == 2 ? cudaFuncSetAttribute(chol_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(chol_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int grid = chol_wave_windows(sm_count);
     if (grid > p.n_windows) grid = p.n_windows;
+    if (nrhs == 2) {
+        chol_solve_kernel<2><<<grid, CH_THREADS, smem, st>>>(smap, p);
+        return cudaGetLastError();
+    }
     static const bool profile = getenv("BP_CHOL_PROFILE") != nullptr;
     if (profile) {
         SolveParams q = p;
@@ -475,7 +551,7 @@ cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int
         if (!dbg) cudaMalloc(&dbg, 6 * sizeof(long long));
         cudaMemsetAsync(dbg, 0, 6 * sizeof(long long), st);
         q.debug = dbg;
-        chol_solve_kernel<<<grid, CH_THREADS, smem, st>>>(smap, q);
+        chol_solve_kernel<1><<<grid, CH_THREADS, smem, st>>>(smap, q);
         long long hostv[6];
         cudaMemcpyAsync(hostv, dbg, sizeof(hostv), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
@@ -485,7 +561,7 @@ cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int
                 tot / p.n_windows);
         return cudaGetLastError();
     }
-    chol_solve_kernel<<<grid, CH_THREADS, smem, st>>>(smap, p);
+    chol_solve_kernel<1><<<grid, CH_THREADS, smem, st>>>(smap, p);
     return cudaGetLastError();
 }
 

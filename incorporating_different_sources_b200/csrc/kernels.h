@@ -9,6 +9,9 @@ namespace bp {
 
 enum { BP_MODE_CONJUGATE = 0, BP_MODE_JEFFREYS = 1 };
 enum { BP_PRIOR_VW = 0, BP_PRIOR_EW = 1 };
+// sibling estimators on the sample moments of the daily window; they run as
+// BP_MODE_JEFFREYS batches whose Gram epilogue centres with 1/m (m = n-1 returns) instead of 1/n
+enum { BP_EST_NONE = 0, BP_EST_JORION = 1, BP_EST_SHRINKAGE = 2 };
 
 // per-window scalar record written by window_prep_kernel / chol_solve_kernel
 enum {
@@ -22,7 +25,17 @@ enum {
     BP_S_SUMA = 7,   // sum_k a_k
     BP_S_V1 = 8,     // w1' S1 w1                    (:574)
     BP_S_MCM_AVG = 9,  // average MCM over the window (:112)
-    BP_S_COUNT = 12
+    BP_S_COUNT = 12,
+    // estimator batches reuse the slots the Jeffreys path leaves at zero (slot 3 stays the Gram's beta)
+    BP_S_JORION_MU_G = 0,          // grand mean mu_g                     (:882)
+    BP_S_JORION_LAMBDA = 1,        // lambda_hat                          (:885)
+    BP_S_JORION_V = 2,             // v_hat                               (:887)
+    BP_S_JORION_Q = 4,             // (mu_hat - mu_g 1)' V_bar^-1 (mu_hat - mu_g 1)
+    BP_S_JORION_ONE_VINV_ONE = 5,  // 1' V_bar^-1 1
+    BP_S_LW_SHRINKAGE = 0,         // Ledoit-Wolf shrinkage intensity
+    BP_S_LW_MU = 1,                // trace(emp_cov) / N
+    BP_S_LW_BETA = 2,              // sklearn's beta (before the min with delta)
+    BP_S_LW_DELTA = 4              // sklearn's delta
 };
 
 struct PrepParams {
@@ -57,6 +70,7 @@ struct PrepParams {
     double* y_ws;             // [W][y_stride] scratch for the HF row dots
     long long y_stride;
     // banded-GEMM form of the daily pass (band_prep.cu), used for batches of consecutive trade dates
+    int beta_den;             // Jeffreys-mode rank-1 coefficient beta = 1 / beta_den (0: n_window, :600; estimators: n-1)
     int use_band;
     double* band_aw;          // [W][band_ld] risk-free weights a_k(w)
     int band_ld;
@@ -102,6 +116,8 @@ struct SolveParams {
     long long win_stride;
     int ldv;
     int mode;                // BP_MODE_*
+    int estimator;           // BP_EST_*: JORION solves two right-hand sides (t and 1) and combines them (:851-895)
+    int n_returns;           // m = n - 1 (Jorion's T)
     double inv_gamma;        // 1 / risk_aversion
     double* S;               // [W][win_stride] in: lower triangle of S1 / J ; out: Cholesky factor
     const double* rhs;       // [W][ldv]
@@ -174,6 +190,22 @@ constexpr int GRAM_KT = 32;        // rows per TMA k-tile
 constexpr int GRAM_TILE = 128;     // output tile edge
 cudaError_t launch_gram(const GramParams& p, const CUtensorMap& map0, const CUtensorMap& map1, int sm_count,
                         cudaStream_t st);
+// Ledoit-Wolf shrinkage of the centred Gram C = X_c'X_c in the solver workspace (in place):
+// S <- (1 - delta) C + delta mu m I, the matrix of Sigma_LW w = mu_hat multiplied by m (sklearn.covariance.ledoit_wolf
+// as called by pypfopt's CovarianceShrinkage.ledoit_wolf(), portfolio_calculations.py:727-729)
+struct ShrinkParams {
+    int n_windows, n_assets, n_window, ld, ldv, ldS;
+    long long win_stride;
+    const double* lr_daily;   // [D][ld]
+    const double* rf_row;     // [D]
+    const int* day_row;       // [W]
+    const int* extra_row;     // [W] or nullptr
+    const int* span_days;     // [W]
+    const double* t;          // [W][ldv]
+    double* S;                // [W][win_stride] lower triangle of C, overwritten
+    double* scal;             // [W][BP_S_COUNT]
+};
+cudaError_t launch_lw_shrink(const ShrinkParams& p, cudaStream_t st);
 cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int sm_count, cudaStream_t st);
 int chol_wave_windows(int sm_count);
 

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(PREP_THREADS, 2) window_prep_kernel(PrepParams
             scal[BP_S_N0] = 0.0;
             scal[BP_S_N1] = 0.0;
             scal[BP_S_ALPHA] = 0.0;
-            scal[BP_S_BETA] = 1.0 / (double)p.n_window;     // J = T - (1/n) t t'  (:600)
+            scal[BP_S_BETA] = 1.0 / (double)(p.beta_den > 0 ? p.beta_den : p.n_window);     // J = T - (1/n) t t'  (:600)
             scal[BP_S_C] = 0.0;
             scal[BP_S_V0] = 0.0;
             scal[BP_S_M] = 0.0;

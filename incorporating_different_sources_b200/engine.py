@@ -313,6 +313,27 @@ class BayesEngine:
         """``calculate_jeffreys_portfolio`` (:838-849) for every window of the batch."""
         return self._run(self._lib.bp_jeffreys_batched, batch, outputs, device_out, into, False)
 
+    def _estimator(self, which: int, batch: WindowBatch, outputs, device_out, into):
+        lib = self._lib
+
+        def fn(h, d, o):
+            return lib.bp_estimator_batched(h, d, which, o)
+        return self._run(fn, batch, outputs, device_out, into, False)
+
+    def jorion(self, batch: WindowBatch, outputs: Sequence[str] = ("weights", "status"),
+               device_out: bool = False, into: Optional[dict] = None) -> Dict[str, object]:
+        """``calculate_jorion_portfolio`` (:851-895) for every window of the batch: one factorisation of the
+        centred Gram, two right-hand sides, Bayes-Stein combination in the solver's epilogue."""
+        from ._lib import EST_JORION
+        return self._estimator(EST_JORION, batch, outputs, device_out, into)
+
+    def shrinkage(self, batch: WindowBatch, outputs: Sequence[str] = ("weights", "status"),
+                  device_out: bool = False, into: Optional[dict] = None) -> Dict[str, object]:
+        """``calculate_shrinkage_portfolio`` (:703-758) in closed form, ``(1/gamma) Sigma_LW^-1 mu_hat`` with the
+        Ledoit-Wolf covariance (unrounded: the reference's ``clean_weights()`` rounding is the facade's job)."""
+        from ._lib import EST_SHRINKAGE
+        return self._estimator(EST_SHRINKAGE, batch, outputs, device_out, into)
+
     def moments(self, batch: WindowBatch, outputs: Sequence[str], jeffreys: bool = False,
                 device_out: bool = False, into: Optional[dict] = None) -> Dict[str, object]:
         """Posterior moments without the solve (t, w0, rhs, scalars, T, S0, S1)."""

@@ -548,6 +548,46 @@ def calculate_jeffreys_portfolio(portfolio_spec, trading_date_ts, k_stock_prices
 
 
 # ----------------------------------------------------------------------------------------------
+# sibling estimators on the same sample moments (:703-758, :851-895)
+# ----------------------------------------------------------------------------------------------
+def calculate_jorion_portfolio(portfolio_spec, trading_date_ts, k_stock_prices_df, risk_free_rate_df):
+    """:851-895 — Jorion's Bayes-Stein portfolio; index named 'Stock' as in the reference (:893)."""
+    N = len(k_stock_prices_df.columns)
+    if portfolio_spec["rolling_window"] - 1 - N - 2 <= 0:
+        raise ValueError("Jorion needs T - N - 2 > 0 (T = rolling_window - 1 returns, :879)")
+    eng, batch, cols = _upload_window(dict(portfolio_spec, weighting_strategy="jeffreys"), trading_date_ts,
+                                      k_stock_prices_df, risk_free_rate_df)
+    res = eng.jorion(batch, outputs=("weights", "status"))
+    _check_status(res["status"][0])
+    return _weight_frame(res["weights"][0], cols, index_name="Stock")
+
+
+def clean_weights(weights, cutoff=1e-4, rounding=5):
+    """pypfopt 1.5.5 ``base_optimizer.clean_weights``: |w| < cutoff -> 0, then round (called at :743)."""
+    w = np.array(weights, dtype=np.float64, copy=True)
+    w[np.abs(w) < cutoff] = 0.0
+    return np.round(w, rounding)
+
+
+def calculate_shrinkage_portfolio(portfolio_spec, trading_date_ts, k_stock_prices_df, risk_free_rate_df,
+                                  clean=True):
+    """:703-758 — Ledoit-Wolf shrinkage tangency weights, index named 'Stock' (:744).
+
+    The reference obtains them from a cvxpy solve (pypfopt ``EfficientFrontier.max_quadratic_utility`` with a
+    zero-variance RISK_FREE column and inactive bounds) and checks them against ``(1/gamma) Sigma^-1 mu`` to
+    1e-4 (:748-756); the device computes that closed form directly and ``clean=True`` applies the
+    ``clean_weights()`` cutoff / 5-decimal rounding the reference returns (:743).  pypfopt and cvxpy are not
+    installed here, so parity of this function is pinned against sklearn's ``ledoit_wolf`` (what pypfopt calls)
+    on the reference's own excess returns, not against the reference's rounded solver output."""
+    eng, batch, cols = _upload_window(dict(portfolio_spec, weighting_strategy="jeffreys"), trading_date_ts,
+                                      k_stock_prices_df, risk_free_rate_df)
+    res = eng.shrinkage(batch, outputs=("weights", "status"))
+    _check_status(res["status"][0])
+    w = res["weights"][0]
+    return _weight_frame(clean_weights(w) if clean else w, cols, index_name="Stock")
+
+
+# ----------------------------------------------------------------------------------------------
 # loop level (:611-658, :941-1238): see backtest.py
 # ----------------------------------------------------------------------------------------------
 from .backtest import (  # noqa: E402,F401

@@ -243,6 +243,77 @@ def jeffreys_window(spec, mkt, d_idx, cols):
     return dict(t=t, T=T, J=J, nu=nu, weights=weights)
 
 
+# --------------------------------------------------------------------------- sibling estimators
+def jorion_window(spec, mkt, d_idx, cols):
+    """``calculate_jorion_portfolio`` (:851-895): Bayes-Stein shrinkage, explicit inverses as in the reference."""
+    cols = np.asarray(cols)
+    t, T_stat, X = daily_statistics(spec, mkt, d_idx, cols)
+    N = len(cols)                                                                       # :869
+    T = len(X)                                                                          # :870
+    mu_hat = X.mean(axis=0)                                                             # :873
+    V_hat = np.cov(X, rowvar=False)                                                     # :876 (ddof = 1)
+    V_bar = T / (T - N - 2) * V_hat                                                     # :879
+    V_bar_inv = np.linalg.inv(V_bar)                                                    # :880
+    one = np.ones(N)
+    one_vinv_one = np.dot(np.dot(one, V_bar_inv), one)
+    mu_g = np.dot(np.dot(one, V_bar_inv), mu_hat) / one_vinv_one                        # :882
+    diff = mu_hat - mu_g * one                                                          # :884
+    q = np.dot(np.dot(diff, V_bar_inv), diff)
+    lam = (N + 2) / q                                                                   # :885
+    v_hat = (N + 2) / ((N + 2) + T * q)                                                 # :887
+    V_PJ = (1 + 1 / (T + lam)) * V_bar + lam / (T * (T + 1 + lam)) * np.outer(one, one) / one_vinv_one   # :888
+    mu_PJ = (1 - v_hat) * mu_hat + v_hat * mu_g * one                                   # :889
+    weights = 1 / spec["risk_aversion"] * np.dot(np.linalg.inv(V_PJ), mu_PJ)            # :891-893
+    return dict(t=t, mu_hat=mu_hat, V_hat=V_hat, mu_g=mu_g, q=q, lambda_hat=lam, v_hat=v_hat,
+                one_vinv_one=one_vinv_one, weights=weights)
+
+
+def ledoit_wolf(X):
+    """``sklearn.covariance.ledoit_wolf(X)`` (scikit-learn >= 0.24 ``_shrunk_covariance.py``: ``ledoit_wolf_shrinkage``
+    + ``_ledoit_wolf``), the routine pypfopt 1.5.5 ``CovarianceShrinkage.ledoit_wolf()`` (constant-variance target)
+    calls on the returns at :727-729.  pypfopt and its call site cannot run here (not installed); this restatement is
+    pinned against the installed sklearn in ``tests/test_oracle_golden.py``.  Returns (shrunk_cov, shrinkage)."""
+    n_samples, n_features = X.shape
+    Xc = X - X.mean(0)
+    X2 = Xc ** 2
+    emp_cov_trace = np.sum(X2, axis=0) / n_samples
+    mu = np.sum(emp_cov_trace) / n_features
+    beta_ = np.sum(np.dot(X2.T, X2))
+    delta_ = np.sum(np.dot(Xc.T, Xc) ** 2) / n_samples ** 2
+    beta = 1.0 / (n_features * n_samples) * (beta_ / n_samples - delta_)
+    delta = (delta_ - 2.0 * mu * emp_cov_trace.sum() + n_features * mu ** 2) / n_features
+    beta = min(beta, delta)
+    shrinkage = 0 if beta == 0 else beta / delta
+    emp_cov = np.dot(Xc.T, Xc) / n_samples
+    shrunk = (1.0 - shrinkage) * emp_cov
+    shrunk.flat[:: n_features + 1] += shrinkage * (np.trace(emp_cov) / n_features)
+    return shrunk, shrinkage
+
+
+ANNUALIZATION = {"daily": 252, "weekly": 52, "monthly": 12}                             # :116-124
+
+
+def shrinkage_window(spec, mkt, d_idx, cols, cov_fn=None):
+    """``calculate_shrinkage_portfolio`` (:703-758) in the closed form of its own CHECK block (:748-756):
+    ``1/gamma * inv(Sigma_LW * f) @ (mu_hat * f)`` with f the annualisation factor.  ``cov_fn`` lets the tests plug in
+    the installed ``sklearn.covariance.ledoit_wolf`` instead of the restatement above."""
+    cols = np.asarray(cols)
+    t, _, X = daily_statistics(spec, mkt, d_idx, cols)
+    f = ANNUALIZATION[spec["rolling_window_frequency"]]
+    mean = X.mean(axis=0) * f                                                           # :721-724 (compounding=False)
+    cov, shrink = (cov_fn or ledoit_wolf)(X)
+    cov = cov * f                                                                       # :727-729
+    weights = 1 / spec["risk_aversion"] * np.dot(np.linalg.inv(cov), mean)              # :750-753
+    return dict(t=t, mean=mean, cov=cov, shrinkage=shrink, weights=weights)
+
+
+def clean_weights(w, cutoff=1e-4, rounding=5):
+    """pypfopt 1.5.5 ``clean_weights`` (:743)."""
+    w = np.array(w, dtype=np.float64, copy=True)
+    w[np.abs(w) < cutoff] = 0
+    return np.round(w, rounding)
+
+
 def cap_order(mkt, d_idx, size, eligible=None):
     """Asset set and ORDER of one window: ``nlargest(size)`` of the caps at d (:653-654, F7)."""
     caps = mkt.caps[d_idx]
@@ -261,6 +332,10 @@ def window_weights(spec, mkt, d_idx, cols=None, hf_lookback_days=None):
         return conjugate_window(spec, mkt, d_idx, cols, hf_lookback_days)["weights"], cols
     if strat == "jeffreys":
         return jeffreys_window(spec, mkt, d_idx, cols)["weights"], cols
+    if strat == "jorion":
+        return jorion_window(spec, mkt, d_idx, cols)["weights"], cols
+    if strat == "shrinkage":
+        return clean_weights(shrinkage_window(spec, mkt, d_idx, cols)["weights"]), cols
     if strat == "vw":
         return prior_w(spec, mkt.caps[d_idx, cols]), cols
     if strat == "ew":

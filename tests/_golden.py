@@ -15,7 +15,12 @@ _market_cache = {}
 def golden_names():
     """Per-window fixtures (the loop-level ``bt_*`` fixtures are handled by test_gpu_backtest.py)."""
     return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                  if not n.startswith("bt_"))
+                  if not n.startswith(("bt_", "est_")))
+
+
+def estimator_golden_names():
+    """Fixtures of the sibling estimators (tests/golden/make_estimator_golden.py)."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "est_*.npz")))
 
 
 def sha(a):
@@ -36,8 +41,8 @@ def market_for(meta):
         mkt = generate_market(**meta["market"])
         # the fixtures are only meaningful if the seeded generator reproduces the same inputs
         assert sha(mkt.prices) == meta["sha_prices"], "synthetic generator drifted: daily prices differ"
-        assert sha(mkt.hf_prices) == meta["sha_hf"], "synthetic generator drifted: intraday prices differ"
-        assert sha(mkt.caps) == meta["sha_caps"], "synthetic generator drifted: caps differ"
+        assert sha(mkt.hf_prices) == meta.get("sha_hf", sha(mkt.hf_prices)), "synthetic generator drifted: intraday prices differ"
+        assert sha(mkt.caps) == meta.get("sha_caps", sha(mkt.caps)), "synthetic generator drifted: caps differ"
         _market_cache[key] = mkt
     return _market_cache[key]
 

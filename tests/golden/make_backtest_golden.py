@@ -35,6 +35,9 @@ CASES = [
     dict(name="bt_conj_weeklywin_monthly_n7", market=dict(n_assets=7, n_days=330, seed=3005),
          spec=spec(size=7, rolling_window=40, rolling_window_frequency="weekly", rebalancing_frequency="monthly"),
          start=-70, end=-2),
+    dict(name="bt_jorion_weekly_top6of9", market=dict(n_assets=9, n_days=120, seed=3006),
+         spec=spec(weighting_strategy="jorion", size=6, rolling_window=45, rebalancing_frequency="weekly",
+                   risk_aversion=4, mcm_scaling=None, display_name="Jorion"), start=-40, end=-2),
     dict(name="bt_vw_daily_top5of9", market=dict(n_assets=9, n_days=60, seed=3004),
          spec=spec(weighting_strategy="vw", size=5, risk_aversion=None, mcm_scaling=None, rolling_window=20,
                    display_name="VW"), start=-15, end=-1),
@@ -43,7 +46,10 @@ CASES = [
 
 def main():
     pc = load_reference(check=True)
+    only = sys.argv[1:]
     for case in CASES:
+        if only and case["name"] not in only:
+            continue
         mkt = generate_market(**case["market"])
         set_universe(mkt.tickers)
         md = mkt.market_data()
