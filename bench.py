@@ -439,6 +439,8 @@ def run_ours(args):
         }
         if n_gpus == 1 and not args.no_cpu:
             line["cpu_baseline"], line["parity_max_rel_err"] = cpu_baseline(args, mkt, conj, jeff, d_idx, out_c, out_j)
+        if n_gpus == 1 and not args.no_widened:
+            line["widened"] = widened_estimators(args, torch, eng, mkt, jeff, d_idx, dgemm_tf, not args.no_cpu)
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
@@ -476,6 +478,59 @@ def cpu_baseline(args, mkt, conj, jeff, d_idx, out_c, out_j):
                        f"oracle/bayes_oracle.py with NumPy's default BLAS threads ({threads})"}, worst)
 
 
+def widened_estimators(args, torch, eng, mkt, jeff, d_idx, dgemm_tf, with_cpu):
+    """SURVEY 8(f) rank 3, measured OUTSIDE the timed region of the headline metric: Jorion (:851-895) and the
+    Ledoit-Wolf shrinkage closed form (:703-758) over the same 4,150 rebalance dates (rolling_window of the Jeffreys
+    leg), device resident, CUDA events; a few windows re-checked against the oracle and timed on the CPU."""
+    from incorporating_different_sources_b200.windows import plan_daily_windows
+    from oracle import bayes_oracle as bo
+    N, W = args.n_assets, len(d_idx)
+    dev = torch.device("cuda", eng.device)
+    out = {"weights": torch.empty((W, N), dtype=torch.float64, device=dev),
+           "status": torch.empty((W,), dtype=torch.int32, device=dev)}
+    res = {}
+    cols = np.arange(N)
+    sel = np.linspace(0, W - 1, 6).round().astype(int)
+    for name, run, oracle in (("jorion", eng.jorion, bo.jorion_window), ("shrinkage", eng.shrinkage, bo.shrinkage_window)):
+        spec = dict(jeff, weighting_strategy=name, display_name=name)
+        batch = plan_daily_windows(spec, mkt.dates, d_idx, need_hf=False)
+        run(batch, outputs=("weights", "status"), into=out)
+        torch.cuda.synchronize()
+        eng.set_stage_timing(True)
+        eng.stage_times()
+        l0 = eng.launch_count
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            run(batch, outputs=("weights", "status"), into=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        st = eng.stage_times()
+        eng.set_stage_timing(False)
+        chol = N ** 3 / 3.0 + (6.0 if name == "jorion" else 4.0) * N * N
+        s_ms = st["solve"]["ms"] / reps
+        r = {"windows_per_s": W / (ms * 1e-3), "ms_per_batch": ms, "windows": W, "rolling_window": jeff["rolling_window"],
+             "gpu_launches": int((eng.launch_count - l0) // reps),
+             "stages_ms": {k: st[k]["ms"] / reps for k in ("prep", "gram", "solve")},
+             "solve_tflops": W * chol / (s_ms * 1e-3) / 1e12 if s_ms > 0 else None,
+             "solve_frac_of_dgemm_peak": W * chol / (s_ms * 1e-3) / 1e12 / dgemm_tf if s_ms > 0 and dgemm_tf > 0 else None,
+             "windows_flagged_singular": int((out["status"] != 0).sum().item())}
+        if with_cpu:
+            w = out["weights"].cpu().numpy()
+            worst = 0.0
+            t0 = time.perf_counter()
+            for i in sel:
+                ref = oracle(spec, mkt, int(d_idx[i]), cols)["weights"]
+                worst = max(worst, float(np.max(np.abs(w[i] - ref)) / np.max(np.abs(ref))))
+            r["cpu_port_windows_per_s"] = len(sel) / (time.perf_counter() - t0)
+            r["parity_max_rel_err"] = worst
+        res[name] = r
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -488,6 +543,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--ref-sample", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-widened", action="store_true", help="skip the Jorion / shrinkage measurements (SURVEY 8(f))")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
