@@ -1058,7 +1058,7 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
                 if (rc) return rc;
             }
             if (estimator == BP_EST_SHRINKAGE) {
-                // C = X_c'X_c  ->  m Sigma_LW = (1 - shrinkage) C + shrinkage mu m I, in place (:727-729)
+                // C = X_c'X_c  ->  m Sigma_LW / (1 - shrinkage) = C + rho I, rhs = t / (1 - shrinkage), in place (:727-729)
                 ShrinkParams q{};
                 q.n_windows = wc;
                 q.n_assets = N;
@@ -1074,6 +1074,7 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
                 q.span_days = B.span + w0;
                 q.t = c.t;
                 q.S = c.S;
+                q.rhs = c.rhs;
                 q.scal = c.scal;
                 StageTimer tm(h, BP_STAGE_PREP);
                 CU_TRY(launch_lw_shrink(q, h->stream));

@@ -191,7 +191,7 @@ constexpr int GRAM_TILE = 128;     // output tile edge
 cudaError_t launch_gram(const GramParams& p, const CUtensorMap& map0, const CUtensorMap& map1, int sm_count,
                         cudaStream_t st);
 // Ledoit-Wolf shrinkage of the centred Gram C = X_c'X_c in the solver workspace (in place):
-// S <- (1 - delta) C + delta mu m I, the matrix of Sigma_LW w = mu_hat multiplied by m (sklearn.covariance.ledoit_wolf
+// S <- C + rho I, rhs <- t / (1 - delta), rho = delta mu m / (1 - delta): Sigma_LW w = mu_hat scaled by m / (1 - delta) (sklearn.covariance.ledoit_wolf
 // as called by pypfopt's CovarianceShrinkage.ledoit_wolf(), portfolio_calculations.py:727-729)
 struct ShrinkParams {
     int n_windows, n_assets, n_window, ld, ldv, ldS;
@@ -202,7 +202,8 @@ struct ShrinkParams {
     const int* extra_row;     // [W] or nullptr
     const int* span_days;     // [W]
     const double* t;          // [W][ldv]
-    double* S;                // [W][win_stride] lower triangle of C, overwritten
+    double* S;                // [W][win_stride] lower triangle of C, diagonal overwritten
+    double* rhs;              // [W][ldv] right-hand side of the solve, overwritten
     double* scal;             // [W][BP_S_COUNT]
 };
 cudaError_t launch_lw_shrink(const ShrinkParams& p, cudaStream_t st);

@@ -60,7 +60,7 @@ def test_gpu_estimators_match_golden(engine, name):
         got = engine.shrinkage(batch, outputs=("weights", "scalars", "status", "S1"))
         assert got["status"][0] == 0
         assert abs(got["scalars"][0][SCAL_LW["shrinkage"]] - float(z[pre + "lw_shrinkage"])) <= TOL * float(z[pre + "lw_shrinkage"])
-        cov = got["S1"][0] / m * f                      # the device factors m * Sigma_LW
+        cov = got["S1"][0] * (1.0 - got["scalars"][0][SCAL_LW["shrinkage"]]) / m * f     # the device factors m Sigma_LW / (1 - shrinkage)
         assert relerr(np.diag(cov), z[pre + "lw_cov_diag"]) <= TOL
         assert relerr(cov[0], z[pre + "lw_cov_row0"]) <= TOL
         assert relerr(got["weights"][0], z[pre + "lw_weights"]) <= TOL
