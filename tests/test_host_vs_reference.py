@@ -1,0 +1,105 @@
+"""Host-side index logic against the UNMODIFIED reference, on the edge cases the domain has: late listings (NaN
+prices inside the look-back), stocks without intraday data, NaN and TIED market caps, a constituent list that names
+unknown tickers, portfolios larger than the eligible universe, partially overlapping turnover frames.
+
+Runs on the CPU (no CUDA call) wherever /root/reference exists; index order and membership are compared exactly.
+"""
+import numpy as np
+import pandas as pd
+import pytest
+
+from incorporating_different_sources_b200 import backtest as bt
+from incorporating_different_sources_b200.synthetic import generate_market
+from oracle.ref_import import load_reference, reference_available, set_universe
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference sources not present on this machine")
+
+
+def _damaged_market():
+    mkt = generate_market(12, 90, seed=4242, bars_per_day=4)
+    md = mkt.market_data()
+    prices, caps, intr = md["stock_prices_df"].copy(), md["stock_market_caps_df"].copy(), md["stock_intraday_prices_df"].copy()
+    t = mkt.tickers
+    prices.iloc[:70, 1] = np.nan                      # late listing: NaN inside a 30-day look-back until day 100
+    prices.iloc[40, 2] = np.nan                       # one hole in the middle of the history
+    intr.iloc[:, 3] = np.nan                          # never traded intraday
+    intr.loc[intr.index >= prices.index[80], t[4]] = np.nan    # intraday feed stops before the last dates
+    caps.iloc[:, 5] = np.nan                          # no market cap at all
+    caps.iloc[:, 6] = caps.iloc[:, 7]                 # exact ties on every date
+    caps = caps.drop(columns=[t[8]])                  # not in the cap frame
+    return mkt, prices, caps, intr
+
+
+@pytest.mark.parametrize("freq", ["daily", "weekly", "monthly"])
+@pytest.mark.parametrize("size", [3, 7, 50])
+def test_universe_selection_matches_reference(freq, size):
+    pc = load_reference(check=True)
+    mkt, prices, caps, intr = _damaged_market()
+    universe = list(mkt.tickers[:11]) + ["ZZZ_UNKNOWN"]          # ticker 11 is not a constituent, one name is unknown
+    set_universe(universe)
+    bt.UNIVERSE_PROVIDER = lambda d: universe
+    try:
+        for pos in (45, 69, 71, 79, 83, 89):
+            d = prices.index[pos]
+            for window_days in (5, 30):
+                ref = pc.get_k_largest_stocks_market_caps(caps, prices, intr, d, size, window_days, freq)
+                got = bt.get_k_largest_stocks_market_caps(caps, prices, intr, d, size, window_days, freq)
+                assert list(got.index) == list(ref.index), (freq, size, pos, window_days)
+                assert np.array_equal(got.to_numpy(), ref.to_numpy())
+                assert got.name == ref.name and got.dtype == ref.dtype
+    finally:
+        bt.UNIVERSE_PROVIDER = None
+
+
+def test_universe_selection_errors_match_reference():
+    pc = load_reference(check=True)
+    mkt, prices, caps, intr = _damaged_market()
+    set_universe(mkt.tickers)
+    d = prices.index[60]
+    for fn in (pc.get_k_largest_stocks_market_caps, bt.get_k_largest_stocks_market_caps):
+        with pytest.raises(RuntimeError):
+            fn(caps, prices, intr, d, 5, 30, "hourly")                              # :637
+        with pytest.raises(ValueError):
+            fn(caps.drop(index=d), prices, intr, d, 5, 30, "daily")                  # :657
+
+
+def test_turnover_and_window_helpers_match_reference():
+    pc = load_reference(check=True)
+    from incorporating_different_sources_b200 import portfolio_calculations as ours
+    rng = np.random.default_rng(3)
+    names = [f"S{i}" for i in range(9)]
+    for _ in range(20):
+        a = rng.choice(names, size=rng.integers(1, 8), replace=False)
+        b = rng.choice(names, size=rng.integers(1, 8), replace=False)
+        before = pd.DataFrame({"Weight": rng.normal(size=len(a))}, index=pd.Index(a, name="Stock"))
+        after = pd.DataFrame({"Weight": rng.normal(size=len(b))}, index=pd.Index(b, name="Stock"))
+        ref = pc.compute_portfolio_turnover(before.copy(), after.copy())
+        assert bt.compute_portfolio_turnover(before, after) == ref
+    for freq in ("daily", "weekly", "monthly"):
+        spec = dict(rolling_window=37, rolling_window_frequency=freq)
+        assert bt.get_window_trading_days(spec) == pc.get_window_trading_days(spec)                  # :126-134
+        assert ours.get_window_annualization_factor(spec) == pc.get_window_annualization_factor(spec)  # :116-124
+
+
+def test_rebalance_calendar_matches_reference_loop():
+    """The rebalance rule lives inside the reference's per-day loop (:1166-1176): replay the loop's own
+    bookkeeping on a calendar with holidays and compare the flagged days."""
+    days = pd.bdate_range("2010-12-20", periods=140)
+    days = days.delete([3, 4, 11, 40, 41, 42, 43, 44, 45, 77])          # holidays, one gap longer than a week
+    for freq in ("daily", "weekly", "monthly"):
+        last, ref = None, []
+        for d in days:                                                   # restated from :1166-1176
+            if last is None:
+                reb = True
+            elif freq == "daily":
+                reb = True
+            elif freq == "weekly":
+                reb = d.weekday() == 2 or (d - last).days > 7
+            else:
+                reb = d.month != last.month
+            ref.append(reb)
+            if reb:
+                last = d
+        assert list(bt.rebalance_flags(days, freq)) == ref
+    with pytest.raises(ValueError):
+        bt.rebalance_flags(days, "yearly")
