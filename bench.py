@@ -333,6 +333,7 @@ def run_ours(args):
     eng.set_stage_timing(True)
     eng.stage_times()
     eng.gram_work()
+    eng.solve_work()
     launches0 = eng.launch_count
     sampler = ClockSampler(local)
     sampler.start()
@@ -348,6 +349,7 @@ def run_ours(args):
     ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     stages = eng.stage_times()
     gwork = eng.gram_work()
+    swork = eng.solve_work()
     eng.set_stage_timing(False)
     launches = (eng.launch_count - launches0) // args.steps + (3 if world > 1 else 0)
     status_bad = int((out_c["status"] != 0).sum().item() + (out_j["status"] != 0).sum().item())
@@ -379,7 +381,14 @@ def run_ours(args):
         gram_exec_flops = 2.0 * npairs * tile * (gwork["k_rows"] + gwork["precompute_rows"]) / k
         gram_add_bytes = gwork["add_blocks"] * npairs * tile * 8.0 / k
         gram_scratch_flops = 2.0 * npairs * tile * gwork["full_rows"] / k
-        solve_tf = work["solve_flops"] / (s_ms * 1e-3) / 1e12 if s_ms > 0 else 0.0
+        c_ms = stages["chain"]["ms"] / k
+        chol_flops = N ** 3 / 3.0 + 4.0 * N * N
+        factored, chained = swork["factored"] / k, swork["chained"] / k
+        # the kernel's own work: only the windows it factorises (Jeffreys windows of consecutive dates are solved
+        # relative to every 8th window by jeffreys_chain_kernel and are NOT charged to the Cholesky kernel)
+        solve_tf = factored * chol_flops / (s_ms * 1e-3) / 1e12 if s_ms > 0 else 0.0
+        groups = factored - W if chained > 0 else 0.0           # Jeffreys base windows = groups of the chain kernel
+        chain_flops = groups * (64.0 * N * N + 2048.0 * N)       # 32 right-hand sides forward + backward, Z'Z
         prof = {}
         try:
             with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
@@ -403,13 +412,18 @@ def run_ours(args):
                     "work really issued runs at executed_frac_of_peak of the measured DGEMM peak",
         }
         solve_roof = {
-            "kernel": "chol_solve_kernel (2 launches per step: conjugate, Jeffreys)",
+            "kernel": "chol_solve_kernel (2 launches per step: every conjugate window, every 8th Jeffreys window)",
+            "windows_factorised_per_step": factored, "windows_solved_relative_to_a_base_per_step": chained,
+            "bytes_per_launch_convention": "8N^2 + 16N per factorised window",
             "bound": "tensor", "achieved": solve_tf, "peak": dgemm_tf, "unit": "TFLOP/s",
             "frac": solve_tf / dgemm_tf if dgemm_tf > 0 else None,
             "traffic": prof.get("solve_dram_bytes_per_launch"),
             "ms_per_step": s_ms, "share_of_step": s_ms / ms if ms > 0 else None,
-            "flops_convention": "SURVEY 8(d): N^3/3 + 4N^2 per window (Cholesky + two triangular solves + v1)",
-            "achieved_gbs_vs_hbm": work["solve_bytes"] / (s_ms * 1e-3) / 1e9 if s_ms > 0 else None,
+            "flops_convention": "SURVEY 8(d): N^3/3 + 4N^2 per FACTORISED window (Cholesky + two triangular solves + v1)",
+            "solve_stage_conventional_tflops": work["solve_flops"] / ((s_ms + c_ms) * 1e-3) / 1e12 if s_ms + c_ms > 0 else None,
+            "solve_stage_note": "conventional = every one of the 2W windows charged a full factorisation, over the time of "
+                                "chol_solve_kernel + jeffreys_chain_kernel; not a utilisation figure",
+            "achieved_gbs_vs_hbm": factored * (8.0 * N * N + 16.0 * N) / (s_ms * 1e-3) / 1e9 if s_ms > 0 else None,
             "hbm_peak_gbs": hbm_peak,
         }
         dominant = solve_roof if s_ms >= g_ms else gram_roof
@@ -434,6 +448,10 @@ def run_ours(args):
                 "prep": {"ms": p_ms, "bound": "hbm", "achieved_gbs": work["prep_bytes"] / (p_ms * 1e-3) / 1e9 if p_ms > 0 else None,
                          "peak_gbs": hbm_peak, "note": "algorithmic bytes: each window charged its own rows; served mostly from L2"},
                 "gram": {"ms": g_ms}, "solve": {"ms": s_ms},
+                "chain": {"ms": c_ms, "kernel": "jeffreys_chain_kernel (one CTA per group of 8 consecutive Jeffreys windows)",
+                          "windows": chained, "groups": groups, "bound": "fp64 pipe (plain DFMA) + latency",
+                          "achieved_tflops": chain_flops / (c_ms * 1e-3) / 1e12 if c_ms > 0 else None,
+                          "flops_convention": "64 N^2 + 2048 N per group: 32 right-hand sides through L and L', and Z'Z"},
             },
             "windows_flagged_singular": status_bad,
         }

@@ -51,6 +51,7 @@ extern "C" {
 #define BP_STAGE_PREP 1       /* per-window O(N K) reductions + scalars :40-57,:90-114,:247-282,:361-430 */
 #define BP_STAGE_GRAM 2       /* batched Gram / covariance (DMMA)       :180-182, :317-318, :358, :600 */
 #define BP_STAGE_SOLVE 3      /* Cholesky + solves + weights            :485-489, :572-575, :602-606  */
+#define BP_STAGE_CHAIN 4      /* Jeffreys windows solved relative to a factorised base window :600-606 */
 
 typedef struct bp_handle bp_handle;
 
@@ -153,6 +154,17 @@ int bp_get_gram_work(bp_handle* h, double* out4);
 /* Smallest batch (windows) for which the Gram kernel reuses precomputed block tiles between overlapping
  * windows; INT_MAX disables the reuse (every window is contracted from scratch). Default 32. */
 int bp_set_reuse_min_windows(bp_handle* h, int min_windows);
+/* Jeffreys batches of CONSECUTIVE trade dates (calculate_mean_jeffreys_posterior_nu, :580-608): consecutive windows
+ * differ by a rank 2k+4 term (k rows in, k rows out, the change of the risk-free adjustment and of t t'/n), so only
+ * every `group`-th window is factorised and the others are solved relative to it by the Woodbury identity (30
+ * triangular solves per group + a small elimination per window instead of a factorisation per window; 3e-14 of the
+ * reference-pinned oracle at N = 500).  group in [2, 8]; 0 or 1 factorises every window.  Default 8.  Batches that
+ * are not consecutive dates, weekly windows, and calls that ask for T / S1 always take the per-window path. */
+int bp_set_jeffreys_chain(bp_handle* h, int group);
+/* Solve-stage work since the previous call (then reset): out2[0] windows factorised, out2[1] windows solved
+ * relative to a base window. */
+int bp_get_solve_work(bp_handle* h, double* out2);
+
 /* Pipelining of bp_upload_market_async against bp_conjugate_batched: an intraday block of at least min_bytes
  * is copied in `segments` pieces (1..8; 1 disables; geometric: 1/2, 1/4, ... of the rows), and the conjugate
  * statistics / Gram stages of the windows whose bars have arrived run while the rest is still on the bus

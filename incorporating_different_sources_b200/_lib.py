@@ -27,10 +27,10 @@ EXPORTED = [
     "bp_jeffreys_batched", "bp_set_stage_timing", "bp_get_stage_times",
     "bp_excess_returns", "bp_quadratic_form", "bp_dense_posterior", "bp_moments_batched",
     "bp_upload_market_async", "bp_backtest_batched", "bp_get_gram_work", "bp_set_reuse_min_windows", "bp_set_upload_pipeline", "bp_set_async_outputs",
-    "bp_set_resampled", "bp_estimator_batched",
+    "bp_set_resampled", "bp_estimator_batched", "bp_set_jeffreys_chain", "bp_get_solve_work",
 ]
 BP_NSTAGE = 8
-STAGES = ("logret", "prep", "gram", "solve")
+STAGES = ("logret", "prep", "gram", "solve", "chain")
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -126,6 +126,8 @@ def load():
     lib.bp_set_resampled.argtypes = [C.c_void_p, C.POINTER(ResampledDesc)]
     lib.bp_get_gram_work.argtypes = [C.c_void_p, c_double_p]
     lib.bp_set_reuse_min_windows.argtypes = [C.c_void_p, C.c_int]
+    lib.bp_set_jeffreys_chain.argtypes = [C.c_void_p, C.c_int]
+    lib.bp_get_solve_work.argtypes = [C.c_void_p, c_double_p]
     lib.bp_set_upload_pipeline.argtypes = [C.c_void_p, C.c_int, C.c_longlong]
     lib.bp_set_async_outputs.argtypes = [C.c_void_p, C.c_int]
     lib.bp_backtest_batched.argtypes = [C.c_void_p, C.POINTER(BacktestDesc)]

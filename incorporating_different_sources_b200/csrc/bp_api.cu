@@ -114,6 +114,11 @@ struct bp_handle {
     int reuse_min_windows = 32;
     // work counters of the Gram stage since the last bp_get_gram_work (bench.py's roofline accounting)
     double work_k_rows = 0, work_add_blocks = 0, work_pre_rows = 0, work_full_rows = 0;
+    // Jeffreys windows of consecutive trade dates: only every chain_group-th window is factorised, the others are
+    // solved relative to it (jeffreys_chain.cu); < 2 disables.  Work counters for bench.py's roofline accounting.
+    int chain_group = 8;
+    int work_stride = 1;               // upload_batch counts the Gram work of every work_stride-th window only
+    double work_factored = 0, work_chained = 0;
     double* prior_n = nullptr;
     int prior_n_cap = 0;
     // banded-GEMM daily pass (band_prep.cu): risk-free weights [W][band_ld] and their sums [W][2]
@@ -476,6 +481,7 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         if (ph == 0 && !need_hf) { plan[ph] = PhasePlan(); continue; }
         long long lo[2] = {1LL << 40, 1LL << 40}, hi[2] = {-(1LL << 40), -(1LL << 40)};
         for (int w = 0; w < W; ++w) {
+            if (w % h->work_stride != 0) continue;      // chain path: only the base windows go through the Gram kernel
             const Split sp = split_of(ph, w);
             if (sp.c_hi > sp.c_lo) { lo[0] = std::min(lo[0], sp.c_lo); hi[0] = std::max(hi[0], sp.c_hi); }
             if (sp.fa_hi > sp.fa_lo) { lo[1] = std::min(lo[1], sp.fa_lo); hi[1] = std::max(hi[1], sp.fa_hi); }
@@ -618,7 +624,7 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             int* dB = gd + (size_t)w * GRAM_DESC_INTS + GRAM_PHASE_INTS;
             dB[0] = dr - (n - 2) + 1; dB[1] = n - 2;       // shared weekly rows
             dB[2] = b->extra_row[w];  dB[3] = 1;           // the trade date's own row
-        } else {
+        } else if (w % h->work_stride == 0) {
             const Split sp = split_rows(dr - n + 2, n - 1, plan[1]);
             int* dB = gd + (size_t)w * GRAM_DESC_INTS + GRAM_PHASE_INTS;
             write_phase_desc(sp, plan[1], dB);
@@ -632,7 +638,7 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         }
         const int* d = gd + (size_t)w * GRAM_DESC_INTS;
         auto r8 = [](int r) { return (r + 7) / 8 * 8; };
-        for (int ph = 0; ph < 2; ++ph) {
+        for (int ph = 0; ph < 2 && w % h->work_stride == 0; ++ph) {
             const int* dp = d + ph * GRAM_PHASE_INTS;
             h->work_k_rows += r8(dp[1]) + r8(dp[3]);
             h->work_add_blocks += dp[5] + dp[7] + dp[9];
@@ -892,11 +898,24 @@ int finish(bp_handle* h) {
 // shared driver of bp_conjugate_batched / bp_jeffreys_batched / bp_stats_batched / bp_hf_cov_batched
 int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, int mode, bool solve, int estimator = BP_EST_NONE) {
     Batch B;
+    // Jeffreys batches of consecutive trade dates: factorise every G-th window only (jeffreys_chain.cu)
+    int G = 0;
+    if (h && b && out && mode == BP_MODE_JEFFREYS && estimator == BP_EST_NONE && solve && !out->T && !out->S0 && !out->S1 &&
+        !b->resampled && h->chain_group >= 2 && b->n_windows >= 2 * h->chain_group && b->day_row && h->has_market &&
+        chain_smem_bytes(h->N) <= (size_t)227 * 1024) {
+        bool consecutive = true;
+        for (int w = 1; consecutive && w < b->n_windows; ++w) consecutive = b->day_row[w] == b->day_row[0] + w;
+        const Layout L0 = make_layout(h, 0);
+        if (consecutive && (size_t)b->n_windows * L0.per_window <= h->ws_limit) G = std::min(h->chain_group, chain_max_group());
+    }
+    if (h) h->work_stride = G >= 2 ? G : 1;
     int rc = upload_batch(h, b, mode == BP_MODE_CONJUGATE, &B);
+    if (h) h->work_stride = 1;
     if (rc) return rc;
     CU_TRY(cudaSetDevice(h->device));
     const Layout L = make_layout(h, B.max_m);
     int Wc = (int)std::min<size_t>((size_t)B.W, std::max<size_t>(1, h->ws_limit / L.per_window));
+    if (Wc < B.W) G = 0;
     // Pipelined against a segmented asynchronous intraday upload: prep + Gram of the windows whose bars have
     // arrived run while the rest is still being copied; the solve follows for all windows at once.
     const bool pipelined = mode == BP_MODE_CONJUGATE && h->hf_pending && h->n_seg > 1 && h->seg_waited < h->n_seg &&
@@ -937,11 +956,12 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
         if ((out->T || out->S1 || solve) && (rc = run_block_precompute(h, B, 1))) return rc;
     }
     // Cholesky + solves of the windows [ws, ws+wn) of the workspace
-    auto solve_range = [&](int ws, int wn) -> int {
+    auto solve_range = [&](int ws, int wn, int stride = 1) -> int {
         if (wn <= 0) return BP_OK;
         const Chunk cs = chunk_at(c, L, ws % Wc);
         SolveParams sp{};
         sp.n_windows = wn;
+        sp.w_stride = stride;
         sp.n_assets = N;
         sp.ldS = L.ldS;
         sp.win_stride = L.win_stride;
@@ -958,13 +978,14 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
         sp.weights = cs.weights;
         sp.status = cs.status;
         CUtensorMap smap;
-        int rcs = make_solve_map(h, &smap, cs.S, (long long)wn * L.rowsS, L.ldS);
+        int rcs = make_solve_map(h, &smap, cs.S, ((long long)(wn - 1) * stride + 1) * L.rowsS, L.ldS);
         if (rcs) return rcs;
         {
             StageTimer tm(h, BP_STAGE_SOLVE);
             CU_TRY(launch_chol_solve(sp, smap, h->sm_count, h->stream));
         }
         h->launches++;
+        h->work_factored += wn;
         return BP_OK;
     };
     int w_solved = 0;          // windows already solved by the pipelined path (full waves, between the upload segments)
@@ -1054,7 +1075,12 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
         }
         if (solve || out->S1) {
             if (!pipelined) {
-                rc = run_gram(h, gram_params(h, B, L, c, w0, wc, mode == BP_MODE_CONJUGATE ? GRAM_S1 : GRAM_J), B.resampled);
+                GramParams gp = gram_params(h, B, L, c, w0, wc, mode == BP_MODE_CONJUGATE ? GRAM_S1 : GRAM_J);
+                if (G >= 2) {                      // base windows only
+                    gp.w_stride = G;
+                    gp.n_windows = (wc + G - 1) / G;
+                }
+                rc = run_gram(h, gp, B.resampled);
                 if (rc) return rc;
             }
             if (estimator == BP_EST_SHRINKAGE) {
@@ -1083,8 +1109,38 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
             rc = emit_sym(h, c.S, L, wc, out->S1 ? out->S1 + om : nullptr);
             if (rc) return rc;
         }
+        if (solve && G >= 2) {
+            // factorise the base windows, then solve the other windows of each group relative to their base
+            if ((rc = solve_range(w0, (wc + G - 1) / G, G))) return rc;
+            ChainParams cp{};
+            cp.n_windows = wc;
+            cp.group = G;
+            cp.n_assets = N;
+            cp.n_window = B.n;
+            cp.ld = h->ld;
+            cp.ldv = L.ldv;
+            cp.ldS = L.ldS;
+            cp.win_stride = L.win_stride;
+            cp.inv_gamma = 1.0 / b->risk_aversion;
+            cp.lr_daily = h->lr_d;
+            cp.day_row = B.day_row + w0;
+            cp.S = c.S;
+            cp.t = c.t;
+            cp.pvec = c.pvec;
+            cp.w1 = c.w1;
+            cp.nu = c.nu;
+            cp.weights = c.weights;
+            cp.scal = c.scal;
+            cp.status = c.status;
+            {
+                StageTimer tm(h, BP_STAGE_CHAIN);
+                CU_TRY(launch_jeffreys_chain(cp, h->stream));
+            }
+            h->launches++;
+            h->work_chained += wc - (wc + G - 1) / G;
+        }
         if (solve) {
-            if ((rc = solve_range(w0 + w_solved, wc - w_solved))) return rc;
+            if (G < 2 && (rc = solve_range(w0 + w_solved, wc - w_solved))) return rc;
             if ((rc = emit_vec(h, c.weights, L, wc, out->weights ? out->weights + ov : nullptr))) return rc;
             if ((rc = emit_vec(h, c.nu, L, wc, out->nu ? out->nu + ov : nullptr))) return rc;
             if ((rc = emit_vec(h, c.w1, L, wc, out->w1 ? out->w1 + ov : nullptr))) return rc;
@@ -1229,6 +1285,21 @@ int bp_get_gram_work(bp_handle* h, double* out4) {
     out4[2] = h->work_pre_rows;     // rows contracted by the block precompute launches
     out4[3] = h->work_full_rows;    // rows a from-scratch contraction of every window would touch
     h->work_k_rows = h->work_add_blocks = h->work_pre_rows = h->work_full_rows = 0;
+    return BP_OK;
+}
+
+int bp_set_jeffreys_chain(bp_handle* h, int group) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    if (group < 0 || group > chain_max_group()) return fail(BP_ERR_INVALID, "group must be in [0, %d]", chain_max_group());
+    h->chain_group = group;
+    return BP_OK;
+}
+
+int bp_get_solve_work(bp_handle* h, double* out2) {
+    if (!h || !out2) return fail(BP_ERR_INVALID, "null argument");
+    out2[0] = h->work_factored;
+    out2[1] = h->work_chained;
+    h->work_factored = h->work_chained = 0;
     return BP_OK;
 }
 

@@ -185,7 +185,8 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
         tlast = tn;                               \
     }
 
-    for (int w = blockIdx.x; w < p.n_windows; w += gridDim.x) {
+    // CTA job q factorises window q * w_stride: the loop runs over the window index itself
+    for (int w = blockIdx.x * max(p.w_stride, 1); w < p.n_windows * max(p.w_stride, 1); w += gridDim.x * max(p.w_stride, 1)) {
         double* S = p.S + (long long)w * p.win_stride;
         const double* rhs = p.rhs + (long long)w * p.ldv;
         const int grow0 = w * rowsS;           // first row of this window in the tensor map

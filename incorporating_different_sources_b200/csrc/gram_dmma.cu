@@ -63,8 +63,9 @@ __device__ __forceinline__ bool group_is_add(int g) { return (g % 5) >= 2; }
 
 __device__ __forceinline__ void job_setup(JobState& js, const GramParams& p, int job, int npairs) {
     js.job = job;
-    const int w = job / npairs;
-    const int pr = job - w * npairs;
+    const int wq = job / npairs;
+    const int pr = job - wq * npairs;
+    const int w = p.w_stride > 1 ? wq * p.w_stride : wq;
     int ti = 0;
     while ((ti + 1) * (ti + 2) / 2 <= pr) ++ti;
     js.w = w;

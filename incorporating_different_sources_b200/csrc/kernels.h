@@ -89,6 +89,8 @@ constexpr int GRAM_BLOCK_TILE_DOUBLES = 128 * 128;   // one stored 128x128 tile,
 
 struct GramParams {
     int n_windows;
+    int w_stride;        // job window q works on window q * w_stride of every per-window array (0 = 1); the Jeffreys
+                         // chain path computes the Gram of the base windows only
     int n_assets;        // N
     int ldS;             // leading dimension of the output matrices
     long long win_stride;    // doubles between consecutive output matrices
@@ -111,6 +113,7 @@ struct GramParams {
 
 struct SolveParams {
     int n_windows;
+    int w_stride;            // CTA job q factorises window q * w_stride (0 = 1), see GramParams::w_stride
     int n_assets;
     int ldS;
     long long win_stride;
@@ -207,6 +210,27 @@ struct ShrinkParams {
     double* scal;             // [W][BP_S_COUNT]
 };
 cudaError_t launch_lw_shrink(const ShrinkParams& p, cudaStream_t st);
+// Jeffreys windows of consecutive trade dates relative to a factorised base window (jeffreys_chain.cu)
+struct ChainParams {
+    int n_windows;           // W, consecutive trade dates: day_row[w] = day_row[0] + w
+    int group;               // windows per group; window g * group is the base (factor in its S slot)
+    int n_assets, n_window, ld, ldv, ldS;
+    long long win_stride;
+    double inv_gamma;
+    const double* lr_daily;  // [D][ld]
+    const int* day_row;      // [W]
+    const double* S;         // [W][win_stride]: the base slots hold the Cholesky factor of J_base
+    const double* t;         // [W][ldv]
+    const double* pvec;      // [W][ldv]
+    double* w1;              // [W][ldv]
+    double* nu;
+    double* weights;
+    double* scal;            // [W][BP_S_COUNT] (writes v1)
+    int* status;             // [W] reads the base's flag, writes the chained windows'
+};
+size_t chain_smem_bytes(int n_assets);
+int chain_max_group();
+cudaError_t launch_jeffreys_chain(const ChainParams& p, cudaStream_t st);
 cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int sm_count, cudaStream_t st);
 int chol_wave_windows(int sm_count);
 

@@ -125,6 +125,21 @@ class BayesEngine:
             _raise(rc)
         return {"k_rows": out[0], "add_blocks": out[1], "precompute_rows": out[2], "full_rows": out[3]}
 
+    def set_jeffreys_chain(self, group: int = 8):
+        """Jeffreys batches of consecutive trade dates factorise only every ``group``-th window and solve the others
+        relative to it (Woodbury, rank 2k+4; ``jeffreys_chain.cu``); 0 or 1 factorises every window."""
+        rc = self._lib.bp_set_jeffreys_chain(self._h, int(group))
+        if rc:
+            _raise(rc)
+
+    def solve_work(self) -> Dict[str, float]:
+        """Windows factorised / solved relative to a base window since the last call."""
+        out = (C.c_double * 2)()
+        rc = self._lib.bp_get_solve_work(self._h, out)
+        if rc:
+            _raise(rc)
+        return {"factored": out[0], "chained": out[1]}
+
     def set_reuse_min_windows(self, n: int):
         """Smallest batch for which overlapping windows share precomputed block Gram tiles (2**31-1 disables)."""
         rc = self._lib.bp_set_reuse_min_windows(self._h, int(n))

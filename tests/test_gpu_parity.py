@@ -341,3 +341,59 @@ def test_gpu_weekly_batched_matches_oracle(engine, n_windows):
         assert relerr(got["weights"][i], ref["weights"]) <= TOL
         refj = bo.jeffreys_window(jspec, mkt, d, cols)
         assert relerr(gotj["weights"][i], refj["weights"]) <= TOL
+
+
+@pytest.mark.parametrize("n_assets,rolling_window,n_windows,group", [
+    (10, 60, 37, 8), (33, 120, 50, 8), (50, 252, 64, 8), (130, 252, 21, 5), (200, 400, 35, 8), (96, 300, 17, 2)])
+def test_gpu_jeffreys_chain_matches_oracle_and_per_window_path(engine, n_assets, rolling_window, n_windows, group):
+    """Jeffreys windows of consecutive dates solved relative to a factorised base window (Woodbury, rank 2k+4)
+    against (i) the oracle, 1e-9, and (ii) the per-window factorisation path of the same library, 1e-11; group sizes
+    that do not divide the batch, N below / not a multiple of the 32-row panel, a group of two."""
+    from incorporating_different_sources_b200.engine import upload_synthetic
+    from incorporating_different_sources_b200.synthetic import generate_market
+    from incorporating_different_sources_b200.windows import plan_daily_windows
+    D = rolling_window + n_windows + 3
+    mkt = generate_market(n_assets, D, seed=8100 + n_assets, bars_per_day=2)
+    spec = dict(weighting_strategy="jeffreys", size=n_assets, risk_aversion=3, turnover_cost=15,
+                rebalancing_frequency="daily", rolling_window=rolling_window, rolling_window_frequency="daily",
+                mcm_scaling=None, display_name="x")
+    d_idx = list(range(D - n_windows, D))
+    cols = np.arange(n_assets)
+    upload_synthetic(engine, mkt)
+    batch = plan_daily_windows(spec, mkt.dates, d_idx, need_hf=False)
+    try:
+        engine.set_jeffreys_chain(0)
+        engine.solve_work()
+        plain = engine.jeffreys(batch, outputs=("weights", "nu", "w1", "scalars", "status"))
+        assert engine.solve_work() == {"factored": float(n_windows), "chained": 0.0}
+        engine.set_jeffreys_chain(group)
+        got = engine.jeffreys(batch, outputs=("weights", "nu", "w1", "scalars", "status"))
+        work = engine.solve_work()
+    finally:
+        engine.set_jeffreys_chain(8)
+    n_base = -(-n_windows // group)
+    assert work == {"factored": float(n_base), "chained": float(n_windows - n_base)}
+    assert not got["status"].any() and not plain["status"].any()
+    for k in ("weights", "nu", "w1"):
+        assert relerr(got[k], plain[k]) <= 1e-11, k
+    assert np.max(np.abs(got["scalars"][:, 8] - plain["scalars"][:, 8]) / np.abs(plain["scalars"][:, 8])) <= 1e-10   # v1
+    for i in (0, 1, group - 1, group, n_windows // 2, n_windows - 2, n_windows - 1):
+        ref = bo.jeffreys_window(spec, mkt, d_idx[i], cols)["weights"]
+        assert relerr(got["weights"][i], ref) <= TOL, f"window {i}"
+
+
+def test_gpu_jeffreys_chain_only_for_consecutive_dates(engine):
+    """Every other date: not consecutive -> per-window path (no window is chained), results still match the oracle."""
+    from incorporating_different_sources_b200.engine import upload_synthetic
+    from incorporating_different_sources_b200.synthetic import generate_market
+    from incorporating_different_sources_b200.windows import plan_daily_windows
+    mkt = generate_market(24, 200, seed=812, bars_per_day=2)
+    spec = dict(weighting_strategy="jeffreys", size=24, risk_aversion=3, turnover_cost=15, rebalancing_frequency="daily",
+                rolling_window=100, rolling_window_frequency="daily", mcm_scaling=None, display_name="x")
+    d_idx = list(range(110, 200, 2))
+    upload_synthetic(engine, mkt)
+    engine.solve_work()
+    got = engine.jeffreys(plan_daily_windows(spec, mkt.dates, d_idx, need_hf=False), outputs=("weights", "status"))
+    assert engine.solve_work()["chained"] == 0.0
+    for i in (0, 7, len(d_idx) - 1):
+        assert relerr(got["weights"][i], bo.jeffreys_window(spec, mkt, d_idx[i], np.arange(24))["weights"]) <= TOL
