@@ -70,8 +70,17 @@ def config_dict(args, n_gpus, conj, jeff, hf_days):
         "jeffreys": {"rolling_window": jeff["rolling_window"]},
         "sharding": f"{n_gpus} independent synthetic path(s), one per GPU; weights all-gathered (NCCL)" if n_gpus > 1
         else "single GPU, one path",
-        "cache": "inputs larger than L2 (1.6 GB intraday prices, 8.8 GB workspace); no flush needed",
+        "cache": "inputs larger than L2 (1.3 GB intraday prices, 8.8 GB workspace); no flush needed",
     }
+
+
+def intraday_config(mkt, conj, d_idx, hf_days):
+    """Which intraday rows belong to the workload (same fields in both arms' ``config``)."""
+    from incorporating_different_sources_b200.windows import plan_daily_windows, trim_intraday
+    lo, hi = trim_intraday(plan_daily_windows(conj, mkt.dates, d_idx, mkt.hf_ts, hf_lookback_days=hf_days))
+    return dict(intraday_rows_uploaded=int(hi - lo), intraday_rows_in_market=int(mkt.hf_prices.shape[0]),
+                intraday_note="bars before the first window's look-back (history only the daily windows need) are "
+                              "read by no window and are not uploaded")
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -196,7 +205,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, 1, conj, jeff, args.hf_days),
+        "config": dict(config_dict(args, 1, conj, jeff, args.hf_days), **intraday_config(mkt, conj, d_idx, args.hf_days)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -230,7 +239,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from incorporating_different_sources_b200.engine import BayesEngine, upload_synthetic
-    from incorporating_different_sources_b200.windows import ffill_rows, plan_daily_windows
+    from incorporating_different_sources_b200.windows import ffill_rows, plan_daily_windows, trim_intraday
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -265,14 +274,18 @@ def run_ours(args):
         return t, v
     keep = []
     host = {}
-    for name, arr in (("prices", mkt.prices), ("caps", mkt.caps), ("hf_prices", mkt.hf_prices),
+    cb = plan_daily_windows(conj, mkt.dates, d_idx, mkt.hf_ts, hf_lookback_days=args.hf_days)
+    jb = plan_daily_windows(jeff, mkt.dates, d_idx, need_hf=False)
+    # the 1,007 days of history before the first rebalance date are read by the DAILY windows only: their intraday
+    # bars belong to no window (the reference never touches them either) and are not uploaded
+    hf_row_lo, hf_row_hi = trim_intraday(cb)
+    hf_used = mkt.hf_prices[hf_row_lo:hf_row_hi]
+    for name, arr in (("prices", mkt.prices), ("caps", mkt.caps), ("hf_prices", hf_used),
                       ("mcm", np.stack([mkt.vix, mkt.epu])), ("rf_row", ffill_rows(mkt.dates, mkt.dates, mkt.rf))):
         t, v = pin(arr)
         keep.append(t)
         host[name] = v
     h2d_bytes = int(sum(v.nbytes for v in host.values()))
-    cb = plan_daily_windows(conj, mkt.dates, d_idx, mkt.hf_ts, hf_lookback_days=args.hf_days)
-    jb = plan_daily_windows(jeff, mkt.dates, d_idx, need_hf=False)
     m_hf = int((cb.hf_hi - cb.hf_lo - 1).max())
 
     eng.upload_market(**host)
@@ -301,17 +314,22 @@ def run_ours(args):
     hs_c, hs_j = hs_ct.numpy(), hs_jt.numpy()
     d2h_bytes = int(hw_cv.nbytes + hw_jv.nbytes + hs_c.nbytes + hs_j.nbytes)
 
+    # segments of the pipelined upload: one solver wave of ready windows per segment, then halves
+    e2e_fractions = eng.plan_upload_fractions(cb, hf_used.shape[0])
+
     def step_e2e():
         # pinned host buffers -> HBM (the 1.6 GB intraday block in segments on the copy stream), Jeffreys first
         # because it does not read intraday data and so overlaps the transfer, then conjugate, pipelined against
         # the remaining segments; the calls only queue work (async outputs), so the host plans the conjugate
         # batch while the GPU runs Jeffreys; weights and status flags are in pinned host memory after synchronize()
         eng.set_async_outputs(True)
+        eng.set_upload_fractions(e2e_fractions)
         eng.upload_market(**host, async_copy=True)
         eng.jeffreys(jb, outputs=("weights", "status"), into={"weights": hw_jv, "status": hs_j})
         eng.conjugate(cb, outputs=("weights", "status"), into={"weights": hw_cv, "status": hs_c})
         eng.synchronize()
         eng.set_async_outputs(False)
+        eng.set_upload_fractions(None)
 
     def barrier():
         torch.cuda.synchronize()
@@ -430,12 +448,13 @@ def run_ours(args):
         other = gram_roof if dominant is solve_roof else solve_roof
         dominant = dict(dominant, peak_source="cuBLAS DGEMM 8192^3 (torch.matmul f64) measured live in this run; "
                                               "MEASURED_PEAKS.json has no FP64 figure")
-        logret_bytes = 8.0 * (mkt.prices.shape[0] + mkt.hf_prices.shape[0]) * (N + eng_ld(N))
+        logret_bytes = 8.0 * (mkt.prices.shape[0] + hf_used.shape[0]) * (N + eng_ld(N))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, n_gpus, conj, jeff, args.hf_days),
+            "config": dict(config_dict(args, n_gpus, conj, jeff, args.hf_days),
+                           **intraday_config(mkt, conj, d_idx, args.hf_days)),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_s * 1e3, "matches_device_path": e2e_match},
@@ -459,9 +478,9 @@ def run_ours(args):
         # figures above cannot be read as > 100 %: every distinct return row enters one symmetric rank-1 update per
         # phase (N(N+1) flops), every window needs its own factorisation and solves; every input element is read once
         # and every weight written once.
-        rows_unique = (mkt.prices.shape[0] - 1) * 2 + (mkt.hf_prices.shape[0] - 1)      # daily rows serve both priors
+        rows_unique = (mkt.prices.shape[0] - 1) * 2 + (hf_used.shape[0] - 1)      # daily rows serve both priors
         lb_flops = rows_unique * float(N) * (N + 1) + work["solve_flops"]
-        lb_bytes = 8.0 * N * (2 * mkt.prices.shape[0] + mkt.hf_prices.shape[0]) + 8.0 * N * 2 * W
+        lb_bytes = 8.0 * N * (2 * mkt.prices.shape[0] + hf_used.shape[0]) + 8.0 * N * 2 * W
         lb_ms = max(lb_flops / (dgemm_tf * 1e12), lb_bytes / (hbm_peak * 1e9)) * 1e3
         line["step_lower_bound"] = {
             "unique_flops": lb_flops, "unique_bytes": lb_bytes,

@@ -171,6 +171,14 @@ int bp_get_solve_work(bp_handle* h, double* out2);
  * (the per-date loop of the reference, main.py:74 -> portfolio_calculations.py:1127, has no such ordering
  * constraint: every date only reads bars up to that date).  Default: 8 segments from 256 MiB. */
 int bp_set_upload_pipeline(bp_handle* h, int segments, long long min_bytes);
+/* Explicit segment boundaries for the next asynchronous uploads: n cumulative row fractions (non-decreasing, the
+ * last segment always ends at the last row); n = 0 restores the geometric default.  Once the kernels are faster than
+ * the bus the best cut is one solver wave (bp_solve_wave_windows) of ready windows per segment with a short last
+ * segment: every segment's windows are then solved at full occupancy while the next segment is on the bus, and only
+ * the last few windows remain after the copy has finished. */
+int bp_set_upload_fractions(bp_handle* h, int n, const double* cum_fractions);
+/* Windows the solver works on concurrently (one CTA each, 6 per SM). */
+int bp_solve_wave_windows(bp_handle* h);
 
 /* Host -> HBM: replaces the pandas frames of get_market_data() (data_handling.py:270-291).  Also
  * computes both log-return matrices on the device (:37, :314). */

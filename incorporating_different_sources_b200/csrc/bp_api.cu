@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <array>
 #include <cstdarg>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -84,6 +85,8 @@ struct bp_handle {
     int pipe_segments = MAX_SEG;
     size_t pipe_min_bytes = (size_t)256 << 20;
     int n_seg = 0, seg_waited = 0;
+    int n_frac = 0;                            // > 0: explicit cumulative row fractions of the segments (bp_set_upload_fractions)
+    double frac[MAX_SEG] = {0};
     long long lr_hf_done = 0;                  // intraday return rows < lr_hf_done have been computed
     long long hf_extra_rows = 0;               // rows allocated behind lr_hf for gathered overnight returns
     int lr_hf_ld_cap = 1;
@@ -137,6 +140,8 @@ struct bp_handle {
     size_t ev_used = 0;
     struct Span { int stage; cudaEvent_t a, b; };
     std::vector<Span> spans;
+    cudaEvent_t ev_t0 = nullptr;       // start of the last upload (BP_TIMELINE=1: spans are printed relative to it)
+    bool t0_armed = false;
 };
 
 namespace {
@@ -1038,6 +1043,8 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
             // occupancy whichever of the copy and the GPU is the bottleneck.
             if (!last) {
                 const int wave = chol_wave_windows(h->sm_count);
+                // (solving partial waves between short tail segments was measured and dropped: a launch costs the
+                // latency of one factorisation, 1.1 ms, however few windows it has)
                 const int wn = (w_done - w_solved) / wave * wave;
                 if (wn > 0) {
                     if ((rc = solve_range(w_solved, wn))) return rc;
@@ -1318,6 +1325,26 @@ int bp_set_upload_pipeline(bp_handle* h, int segments, long long min_bytes) {
     return BP_OK;
 }
 
+int bp_set_upload_fractions(bp_handle* h, int n, const double* cum_fractions) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    if (n <= 0 || !cum_fractions) {
+        h->n_frac = 0;
+        return BP_OK;
+    }
+    if (n > bp_handle::MAX_SEG) return fail(BP_ERR_INVALID, "at most %d segments", bp_handle::MAX_SEG);
+    double prev = 0.0;
+    for (int i = 0; i < n; ++i) {
+        if (!(cum_fractions[i] >= prev) || cum_fractions[i] > 1.0)
+            return fail(BP_ERR_INVALID, "cumulative fractions must be non-decreasing in [0, 1]");
+        prev = cum_fractions[i];
+    }
+    for (int i = 0; i < n; ++i) h->frac[i] = cum_fractions[i];
+    h->n_frac = n;
+    return BP_OK;
+}
+
+int bp_solve_wave_windows(bp_handle* h) { return h ? chol_wave_windows(h->sm_count) : 0; }
+
 int bp_set_stage_timing(bp_handle* h, int enable) {
     if (!h) return fail(BP_ERR_INVALID, "null handle");
     h->timing = enable != 0;
@@ -1331,12 +1358,19 @@ int bp_get_stage_times(bp_handle* h, double* ms, long long* launches) {
         ms[i] = 0.0;
         launches[i] = 0;
     }
+    static const bool timeline = getenv("BP_TIMELINE") != nullptr;
     for (const auto& sp : h->spans) {
         float t = 0.f;
         CU_TRY(cudaEventElapsedTime(&t, sp.a, sp.b));
         ms[sp.stage] += (double)t;
         launches[sp.stage] += 1;
+        if (timeline) {
+            float t0 = 0.f;
+            if (cudaEventElapsedTime(&t0, h->t0_armed ? h->ev_t0 : h->spans.front().a, sp.a) != cudaSuccess) t0 = -1.f;
+            fprintf(stderr, "[timeline] stage %d start %8.3f ms dur %7.3f ms\n", sp.stage, t0, t);
+        }
     }
+    (void)cudaGetLastError();
     h->spans.clear();
     h->ev_used = 0;
     return BP_OK;
@@ -1406,6 +1440,11 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
     h->N = N; h->D = D; h->ld = ld; h->R = R; h->n_mcm = m->n_mcm;
     h->has_caps = m->caps != nullptr;
     cudaStream_t st = h->stream;
+    if (h->timing) {
+        if (!h->ev_t0) CU_TRY(cudaEventCreate(&h->ev_t0));
+        CU_TRY(cudaEventRecord(h->ev_t0, st));
+        h->t0_armed = true;
+    }
     // the copy stream must not overwrite buffers that earlier launches on the compute stream still read
     CU_TRY(cudaEventRecord(h->ev_main, st));
     CU_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_main, 0));
@@ -1424,13 +1463,16 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
         // asynchronous uploads of a large block go in segments with an event each; the log returns of a segment
         // are computed on the compute stream by its first consumer (wait_hf / the pipelined conjugate path)
         int nseg = 1;
-        if (!blocking && sizeof(double) * (size_t)R * N >= h->pipe_min_bytes && R >= 64) nseg = h->pipe_segments;
+        if (!blocking && sizeof(double) * (size_t)R * N >= h->pipe_min_bytes && R >= 64)
+            nseg = h->n_frac > 0 ? h->n_frac : h->pipe_segments;
         // geometric segments (1/2, 1/4, ... of the rows): whatever the compute stream is busy with when the copy
         // starts, little work is left to do after the LAST segment has arrived
         long long r1 = 0;
         for (int s = 0; s < nseg; ++s) {
             const long long r0 = r1;
             r1 = s == nseg - 1 ? R : std::max(r0, R - (R >> (s + 1)));
+            if (h->n_frac > 0 && s < nseg - 1)
+                r1 = std::min<long long>(R, std::max<long long>(r0, (long long)std::ceil(h->frac[s] * (double)R)));
             CU_TRY(cudaMemcpyAsync(h->hf_prices + (size_t)r0 * N, m->hf_prices + (size_t)r0 * N, sizeof(double) * (size_t)(r1 - r0) * N,
                                    cudaMemcpyHostToDevice, h->copy_stream));
             if (nseg > 1) {

@@ -159,6 +159,43 @@ class BayesEngine:
         if rc:
             _raise(rc)
 
+    def set_upload_fractions(self, cum_fractions=None):
+        """Explicit cumulative row fractions of the segments of the next asynchronous intraday uploads (at most 8;
+        ``None`` restores the geometric default)."""
+        if cum_fractions is None or len(cum_fractions) == 0:
+            rc = self._lib.bp_set_upload_fractions(self._h, 0, None)
+        else:
+            arr = (C.c_double * len(cum_fractions))(*[float(x) for x in cum_fractions])
+            rc = self._lib.bp_set_upload_fractions(self._h, len(cum_fractions), arr)
+        if rc:
+            _raise(rc)
+
+    def solve_wave_windows(self) -> int:
+        """Windows the solver factorises concurrently (6 per SM)."""
+        return int(self._lib.bp_solve_wave_windows(self._h))
+
+    def plan_upload_fractions(self, batch: WindowBatch, n_hf_rows: int, max_segments: int = 8):
+        """Segment boundaries for a date-sorted conjugate batch: whole solver waves of windows per segment, so that
+        every segment is solved at full occupancy while the next one is on the bus and less than one wave is left
+        when the copy ends.  Returns cumulative row fractions for :meth:`set_upload_fractions`."""
+        wave = self.solve_wave_windows()
+        W = batch.n_windows
+        hi = np.asarray(batch.hf_hi, dtype=np.int64)
+        if W < 2 * wave or np.any(np.diff(hi) < 0):
+            return None
+        # whole waves per segment (several when there are more waves than segments), the remainder as the last one:
+        # a solver launch costs the latency of one factorisation however few windows it has, so short tail segments
+        # only add launches (measured: halving the remainder made the step 6 ms slower)
+        full = W // wave
+        per = -(-full // (max_segments - 1))
+        counts = [per * wave] * (full // per)
+        if full % per:
+            counts.append((full % per) * wave)
+        if W - full * wave > 0:
+            counts.append(W - full * wave)
+        ends = np.cumsum(counts)
+        return [float(hi[e - 1]) / float(n_hf_rows) for e in ends]
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.bp_launch_count(self._h))

@@ -114,6 +114,18 @@ def plan_daily_windows(spec, dates: np.ndarray, d_indices: Sequence[int], hf_ts:
     )
 
 
+def trim_intraday(batch: WindowBatch):
+    """Row range ``[lo, hi)`` of the intraday matrix that the windows of ``batch`` read; the batch is shifted in place
+    so that it refers to ``hf_prices[lo:hi]``.  Bars outside the range (e.g. the years of history before the first
+    rebalance date that only the DAILY windows need) are never touched by any window and need not be uploaded."""
+    if batch.hf_lo is None or batch.hf_hi is None:
+        raise ValueError("this batch has no intraday window rows")
+    lo, hi = int(batch.hf_lo.min()), int(batch.hf_hi.max())
+    batch.hf_lo = (batch.hf_lo - lo).astype(np.int32)
+    batch.hf_hi = (batch.hf_hi - lo).astype(np.int32)
+    return lo, hi
+
+
 @dataclass
 class ResampledRows:
     """Return rows of weekly windows, built on the device from the daily prices (``bp_set_resampled``):

@@ -198,7 +198,8 @@ def test_gpu_async_upload_matches_blocking(engine):
         assert np.array_equal(got, ref)
 
 @pytest.mark.parametrize("segments,order,n_days", [(2, "sorted", 200), (5, "sorted", 200), (8, "sorted", 200),
-                                                   (8, "shuffled", 200), (8, "sorted", 1100)])
+                                                   (8, "shuffled", 200), (8, "sorted", 1100), ("waves", "sorted", 2000),
+                                                   ([0.1, 0.1, 0.55, 0.9], "sorted", 200)])
 def test_gpu_pipelined_upload_matches_blocking(engine, segments, order, n_days):
     """Segmented asynchronous intraday upload: the conjugate statistics / Gram stages of the windows whose bars
     have arrived run while later segments are still being copied.  Same kernels, same descriptors: bit-identical
@@ -221,7 +222,14 @@ def test_gpu_pipelined_upload_matches_blocking(engine, segments, order, n_days):
     engine.upload_market(**arrays)
     ref = engine.conjugate(batch, outputs=outs)
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in arrays.items()}
-    engine.set_upload_pipeline(segments, 0)
+    if isinstance(segments, int):
+        engine.set_upload_pipeline(segments, 0)
+    else:
+        # explicit boundaries: wave-aligned (one solver wave of ready windows per segment, then halves) or given
+        engine.set_upload_pipeline(8, 0)
+        fr = engine.plan_upload_fractions(batch, mkt.hf_prices.shape[0]) if segments == "waves" else segments
+        assert fr is not None and len(fr) <= 8 and all(b >= a for a, b in zip(fr, fr[1:]))
+        engine.set_upload_fractions(fr)
     try:
         for _ in range(2):
             engine.upload_market(**{k: v.numpy() for k, v in pinned.items()}, async_copy=True)
@@ -240,6 +248,7 @@ def test_gpu_pipelined_upload_matches_blocking(engine, segments, order, n_days):
         assert np.array_equal(n0a, n0b) and np.array_equal(s0a, s0b)
     finally:
         engine.set_upload_pipeline()
+        engine.set_upload_fractions(None)
 
 def test_gpu_async_outputs_match_blocking(engine):
     """bp_set_async_outputs: batched calls with page-locked host outputs return once queued (so the host plans the
