@@ -549,6 +549,7 @@ def widened_estimators(args, torch, eng, mkt, jeff, d_idx, dgemm_tf, with_cpu):
         torch.cuda.synchronize()
         eng.set_stage_timing(True)
         eng.stage_times()
+        eng.solve_work()
         l0 = eng.launch_count
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
@@ -560,14 +561,17 @@ def widened_estimators(args, torch, eng, mkt, jeff, d_idx, dgemm_tf, with_cpu):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         st = eng.stage_times()
+        sw = eng.solve_work()
         eng.set_stage_timing(False)
         chol = N ** 3 / 3.0 + (6.0 if name == "jorion" else 4.0) * N * N
         s_ms = st["solve"]["ms"] / reps
+        fact = sw["factored"] / reps
         r = {"windows_per_s": W / (ms * 1e-3), "ms_per_batch": ms, "windows": W, "rolling_window": jeff["rolling_window"],
              "gpu_launches": int((eng.launch_count - l0) // reps),
-             "stages_ms": {k: st[k]["ms"] / reps for k in ("prep", "gram", "solve")},
-             "solve_tflops": W * chol / (s_ms * 1e-3) / 1e12 if s_ms > 0 else None,
-             "solve_frac_of_dgemm_peak": W * chol / (s_ms * 1e-3) / 1e12 / dgemm_tf if s_ms > 0 and dgemm_tf > 0 else None,
+             "stages_ms": {k: st[k]["ms"] / reps for k in ("prep", "gram", "solve", "chain")},
+             "windows_factorised": fact, "windows_solved_relative_to_a_base": sw["chained"] / reps,
+             "solve_tflops": fact * chol / (s_ms * 1e-3) / 1e12 if s_ms > 0 else None,
+             "solve_frac_of_dgemm_peak": fact * chol / (s_ms * 1e-3) / 1e12 / dgemm_tf if s_ms > 0 and dgemm_tf > 0 else None,
              "windows_flagged_singular": int((out["status"] != 0).sum().item())}
         if with_cpu:
             w = out["weights"].cpu().numpy()

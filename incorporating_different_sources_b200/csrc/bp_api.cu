@@ -905,7 +905,7 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
     Batch B;
     // Jeffreys batches of consecutive trade dates: factorise every G-th window only (jeffreys_chain.cu)
     int G = 0;
-    if (h && b && out && mode == BP_MODE_JEFFREYS && estimator == BP_EST_NONE && solve && !out->T && !out->S0 && !out->S1 &&
+    if (h && b && out && mode == BP_MODE_JEFFREYS && (estimator == BP_EST_NONE || estimator == BP_EST_JORION) && solve && !out->T && !out->S0 && !out->S1 &&
         !b->resampled && h->chain_group >= 2 && b->n_windows >= 2 * h->chain_group && b->day_row && h->has_market &&
         chain_smem_bytes(h->N) <= (size_t)227 * 1024) {
         bool consecutive = true;
@@ -1124,6 +1124,7 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
             cp.group = G;
             cp.n_assets = N;
             cp.n_window = B.n;
+            cp.estimator = estimator;
             cp.ld = h->ld;
             cp.ldv = L.ldv;
             cp.ldS = L.ldS;

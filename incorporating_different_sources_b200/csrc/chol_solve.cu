@@ -40,6 +40,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "jorion_math.cuh"
 #include "kernels.h"
 
 namespace bp {
@@ -439,12 +440,7 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
         // ---------------- posterior scalars and weights
         double* scal = p.scal + (long long)w * BP_S_COUNT;
         if constexpr (NRHS == 2) {
-            // Jorion's Bayes-Stein estimator (:851-895) from y = C^-1 t and z = C^-1 1, C = (m-1) V_hat the centred
-            // Gram of the m excess returns:  V_bar = kappa C, kappa = m / ((m-N-2)(m-1))  (:876-879);
-            //   mu_g = 1'V_bar^-1 mu_hat / 1'V_bar^-1 1 (:882), q = (mu_hat - mu_g 1)' V_bar^-1 (mu_hat - mu_g 1),
-            //   lambda = (N+2)/q (:885), v = (N+2)/((N+2) + m q) (:887),
-            //   V_PJ = a V_bar + b 11', a = 1 + 1/(m+lambda), b = lambda / (m (m+1+lambda) 1'V_bar^-1 1) (:888),
-            //   mu_PJ = (1-v) mu_hat + v mu_g 1 (:889), weights = (1/gamma) V_PJ^-1 mu_PJ (:891-893) by Sherman-Morrison.
+            // Jorion's Bayes-Stein estimator (:851-895) from y = C^-1 t and z = C^-1 1: see jorion_math.cuh
             const double* y = xs;
             const double* z = xs + Nr;
             double sy = 0.0, sz = 0.0, ty = 0.0;
@@ -456,37 +452,23 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
             sy = block_sum(sy, scratch);
             sz = block_sum(sz, scratch);
             ty = block_sum(ty, scratch);
-            const double m = (double)p.n_returns, Nd = (double)N;
-            const double kappa = m / ((m - Nd - 2.0) * (m - 1.0));
-            const double sym = sy / m;                               // 1'C^-1 mu_hat
-            const double mu_g = sym / sz;
-            const double q = (ty / (m * m) - sym * sym / sz) / kappa;
-            const double lambda = (Nd + 2.0) / q;
-            const double v = (Nd + 2.0) / ((Nd + 2.0) + m * q);
-            const double a = 1.0 + 1.0 / (m + lambda);
-            const double one_vinv_one = sz / kappa;
-            const double b = lambda / (m * (m + 1.0 + lambda)) / one_vinv_one;
-            const double iak = 1.0 / (a * kappa);
-            const double one_r = sym * iak;                          // 1'(aV_bar)^-1 mu_PJ  (since mu_g 1'z = 1'y/m)
-            const double one_s = sz * iak;                           // 1'(aV_bar)^-1 1
-            const double corr = b * one_r / (1.0 + b * one_s);
+            const JorionCoef jc = jorion_coefficients(sy, sz, ty, (double)p.n_returns, (double)N);
             for (int j = tid; j < p.ldv; j += CH_THREADS) {
                 double yj = 0.0, nu = 0.0;
                 if (j < N) {
                     yj = y[j];
-                    const double rj = ((1.0 - v) * (yj / m) + v * mu_g * z[j]) * iak;
-                    nu = rj - corr * (z[j] * iak);
+                    nu = jc.c_y * yj + jc.c_z * z[j];
                 }
                 p.w1[(long long)w * p.ldv + j] = yj;
                 p.nu[(long long)w * p.ldv + j] = nu;
                 p.weights[(long long)w * p.ldv + j] = p.inv_gamma * nu;
             }
             if (tid == 0) {
-                scal[BP_S_JORION_MU_G] = mu_g;
-                scal[BP_S_JORION_LAMBDA] = lambda;
-                scal[BP_S_JORION_V] = v;
-                scal[BP_S_JORION_Q] = q;
-                scal[BP_S_JORION_ONE_VINV_ONE] = one_vinv_one;
+                scal[BP_S_JORION_MU_G] = jc.mu_g;
+                scal[BP_S_JORION_LAMBDA] = jc.lambda;
+                scal[BP_S_JORION_V] = jc.v;
+                scal[BP_S_JORION_Q] = jc.q;
+                scal[BP_S_JORION_ONE_VINV_ONE] = jc.one_vinv_one;
             }
         } else {
         double mult = 1.0;

@@ -21,6 +21,7 @@
 // then all warps subtract its contribution from the remaining panels (thread = 4 rows x 1 right-hand side, the solved
 // panel column in registers, factor entries as shared-memory broadcasts).
 #include "common.cuh"
+#include "jorion_math.cuh"
 #include "kernels.h"
 
 namespace bp {
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(CH_T, 1) jeffreys_chain_kernel(const ChainPara
     double* Y = csm;                         // [Nr][LDY]
     double* Lb = Y + (size_t)Nr * LDY;       // [NBUF][32][32]
     double* Wm = Lb + NBUF * 32 * 32;        // [32][LDY]
-    double* csol = Wm + 32 * LDY;            // [CH_W][32] small-system solutions
+    double* csol = Wm + 32 * LDY;            // [CH_W][2][32] small-system solutions (two right-hand sides)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x;
@@ -73,6 +74,8 @@ __global__ void __launch_bounds__(CH_T, 1) jeffreys_chain_kernel(const ChainPara
     const int nb = gsize - 1;                                    // chained windows
     if (nb <= 0) return;
     const int n = p.n_window;
+    const bool jorion = p.estimator == BP_EST_JORION;
+    const double beta_den = jorion ? (double)(n - 1) : (double)n;      // rank-1 coefficient 1/n (:600) or 1/m (sample covariance)
     const long long day_b = p.day_row[b];
     const double* L = p.S + (long long)b * p.win_stride;
 
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(CH_T, 1) jeffreys_chain_kernel(const ChainPara
             return COL_T0;
         };
         const int tcol = COL_T + (k - 1);
-        double row[MMAX + 1];
+        double row[MMAX + 2];
         const bool active = lane < m;
         const int mycol = active ? col_of(lane) : 0;
 #pragma unroll
@@ -265,14 +268,15 @@ __global__ void __launch_bounds__(CH_T, 1) jeffreys_chain_kernel(const ChainPara
                 if (c == lane) {
                     if (lane < k) v += 1.0;
                     else if (lane < 2 * k) v -= 1.0;
-                    else if (lane == 2 * k + 2) v -= (double)n;
-                    else if (lane == 2 * k + 3) v += (double)n;
+                    else if (lane == 2 * k + 2) v -= beta_den;
+                    else if (lane == 2 * k + 3) v += beta_den;
                 }
                 if ((lane == 2 * k && c == 2 * k + 1) || (lane == 2 * k + 1 && c == 2 * k)) v -= 1.0;
             }
             row[c] = v;
         }
         row[MMAX] = active ? Wm[mycol * LDY + tcol] : 0.0;       // right-hand side U'y_t
+        row[MMAX + 1] = active ? Wm[mycol * LDY + COL_ONE] : 0.0;    // second right-hand side U'y_1 (Jorion: C^-1 1)
         bool done = !active;
         int mypiv = -1;
         bool singular = false;
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(CH_T, 1) jeffreys_chain_kernel(const ChainPara
                 const double pv = __shfl_sync(0xffffffffu, row[s], bl);
                 const double f = (lane == bl || !active) ? 0.0 : row[s] / pv;
 #pragma unroll
-                for (int c = 0; c <= MMAX; ++c) {
+                for (int c = 0; c <= MMAX + 1; ++c) {
                     if (c > s) {
                         const double pr = __shfl_sync(0xffffffffu, row[c], bl);
                         row[c] = fma(-f, pr, row[c]);
@@ -303,33 +307,74 @@ __global__ void __launch_bounds__(CH_T, 1) jeffreys_chain_kernel(const ChainPara
             }
         }
         // solution component mypiv = rhs / pivot, held by the lane that pivoted on it
-        double* cs = csol + warp * 32;
+        double* cs = csol + warp * 64;            // [2][32]: solutions for the two right-hand sides
         if (active) {
             double piv = 1.0;
 #pragma unroll
             for (int s = 0; s < MMAX; ++s) if (s == mypiv) piv = row[s];
-            if (mypiv >= 0) cs[mypiv] = row[MMAX] / piv;
+            if (mypiv >= 0) {
+                cs[mypiv] = row[MMAX] / piv;
+                cs[32 + mypiv] = row[MMAX + 1] / piv;
+            }
         }
         __syncwarp();
         const long long w = b + k;
         const double* tk = p.t + w * p.ldv;
-        double v1 = 0.0;
-        for (int j = lane; j < p.ldv; j += 32) {
-            double x = 0.0;
-            if (j < N) {
-                x = Y[j * LDY + tcol];
-                for (int a = 0; a < m; ++a) x = fma(-cs[a], Y[j * LDY + col_of(a)], x);
-                v1 = fma(x, tk[j], v1);
+        const int sb = p.status[b];
+        if (!jorion) {
+            double v1 = 0.0;
+            for (int j = lane; j < p.ldv; j += 32) {
+                double x = 0.0;
+                if (j < N) {
+                    x = Y[j * LDY + tcol];
+                    for (int a = 0; a < m; ++a) x = fma(-cs[a], Y[j * LDY + col_of(a)], x);
+                    v1 = fma(x, tk[j], v1);
+                }
+                p.w1[w * p.ldv + j] = x;
+                p.nu[w * p.ldv + j] = x;
+                p.weights[w * p.ldv + j] = p.inv_gamma * x;
             }
-            p.w1[w * p.ldv + j] = x;
-            p.nu[w * p.ldv + j] = x;
-            p.weights[w * p.ldv + j] = p.inv_gamma * x;
-        }
-        v1 = warp_sum(v1);
-        if (lane == 0) {
-            p.scal[w * BP_S_COUNT + BP_S_V1] = v1;
-            const int sb = p.status[b];
-            p.status[w] = sb != 0 ? sb : (singular || !(v1 > 0.0) ? N + 1 : 0);
+            v1 = warp_sum(v1);
+            if (lane == 0) {
+                p.scal[w * BP_S_COUNT + BP_S_V1] = v1;
+                p.status[w] = sb != 0 ? sb : (singular || !(v1 > 0.0) ? N + 1 : 0);
+            }
+        } else {
+            // y = C^-1 t and z = C^-1 1 of this window (kept in w1 / nu for the second pass), then the Bayes-Stein weights
+            double sy = 0.0, sz = 0.0, ty = 0.0;
+            for (int j = lane; j < N; j += 32) {
+                double y = Y[j * LDY + tcol], z1 = Y[j * LDY + COL_ONE];
+                for (int a = 0; a < m; ++a) {
+                    const double ya = Y[j * LDY + col_of(a)];
+                    y = fma(-cs[a], ya, y);
+                    z1 = fma(-cs[32 + a], ya, z1);
+                }
+                p.w1[w * p.ldv + j] = y;
+                p.nu[w * p.ldv + j] = z1;
+                sy += y;
+                sz += z1;
+                ty = fma(tk[j], y, ty);
+            }
+            sy = warp_sum(sy);
+            sz = warp_sum(sz);
+            ty = warp_sum(ty);
+            const JorionCoef jc = jorion_coefficients(sy, sz, ty, (double)(n - 1), (double)N);
+            for (int j = lane; j < p.ldv; j += 32) {
+                double nu = 0.0;
+                if (j < N) nu = jc.c_y * p.w1[w * p.ldv + j] + jc.c_z * p.nu[w * p.ldv + j];     // own writes of this lane
+                else p.w1[w * p.ldv + j] = 0.0;
+                p.nu[w * p.ldv + j] = nu;
+                p.weights[w * p.ldv + j] = p.inv_gamma * nu;
+            }
+            if (lane == 0) {
+                double* sc = p.scal + w * BP_S_COUNT;
+                sc[BP_S_JORION_MU_G] = jc.mu_g;
+                sc[BP_S_JORION_LAMBDA] = jc.lambda;
+                sc[BP_S_JORION_V] = jc.v;
+                sc[BP_S_JORION_Q] = jc.q;
+                sc[BP_S_JORION_ONE_VINV_ONE] = jc.one_vinv_one;
+                p.status[w] = sb != 0 ? sb : (singular || !(ty > 0.0) ? N + 1 : 0);
+            }
         }
         __syncwarp();
     }
@@ -337,7 +382,7 @@ __global__ void __launch_bounds__(CH_T, 1) jeffreys_chain_kernel(const ChainPara
 
 size_t chain_smem_bytes(int n_assets) {
     const int Nr = (n_assets + 31) / 32 * 32;
-    return sizeof(double) * ((size_t)Nr * LDY + NBUF * 32 * 32 + 32 * LDY + CH_W * 32 + 40);
+    return sizeof(double) * ((size_t)Nr * LDY + NBUF * 32 * 32 + 32 * LDY + CH_W * 64 + 40);
 }
 
 int chain_max_group() { return CG_MAX; }

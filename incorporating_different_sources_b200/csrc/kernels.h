@@ -215,6 +215,8 @@ struct ChainParams {
     int n_windows;           // W, consecutive trade dates: day_row[w] = day_row[0] + w
     int group;               // windows per group; window g * group is the base (factor in its S slot)
     int n_assets, n_window, ld, ldv, ldS;
+    int estimator;           // BP_EST_NONE: Jeffreys (J = T - tt'/n, :600); BP_EST_JORION: C = T - tt'/m, m = n-1, and the
+                             // Bayes-Stein combination of C^-1 t and C^-1 1 (:851-895)
     long long win_stride;
     double inv_gamma;
     const double* lr_daily;  // [D][ld]

@@ -147,3 +147,35 @@ def test_facade_jorion_and_shrinkage_frames():
     assert relerr(raw["Weight"].to_numpy(), z["w0_lw_weights"]) <= TOL
     with pytest.raises(ValueError):                                    # last row must be the trading date (:145)
         pc.calculate_jorion_portfolio(spec, d - pd.Timedelta(days=1), prices_df, rf_df)
+
+
+@pytest.mark.parametrize("n_assets,rolling_window,n_windows", [(20, 80, 45), (75, 200, 26)])
+def test_jorion_chain_matches_per_window_path(engine, n_assets, rolling_window, n_windows):
+    """Jorion batches of consecutive dates factorise every 8th window and obtain C^-1 t and C^-1 1 of the others by the
+    Woodbury identity (jeffreys_chain.cu): same weights and Bayes-Stein scalars as the per-window path (1e-10)."""
+    from incorporating_different_sources_b200._lib import SCAL_JORION
+    from incorporating_different_sources_b200.engine import upload_synthetic
+    from incorporating_different_sources_b200.synthetic import generate_market
+    from incorporating_different_sources_b200.windows import plan_daily_windows
+    D = rolling_window + n_windows + 2
+    mkt = generate_market(n_assets, D, seed=6500 + n_assets, bars_per_day=2)
+    spec = dict(weighting_strategy="jorion", size=n_assets, risk_aversion=2, turnover_cost=15,
+                rebalancing_frequency="daily", rolling_window=rolling_window, rolling_window_frequency="daily",
+                mcm_scaling=None, display_name="x")
+    upload_synthetic(engine, mkt)
+    batch = plan_daily_windows(spec, mkt.dates, list(range(D - n_windows, D)), need_hf=False)
+    try:
+        engine.set_jeffreys_chain(0)
+        plain = engine.jorion(batch, outputs=("weights", "w1", "scalars", "status"))
+        engine.set_jeffreys_chain(8)
+        engine.solve_work()
+        got = engine.jorion(batch, outputs=("weights", "w1", "scalars", "status"))
+        work = engine.solve_work()
+    finally:
+        engine.set_jeffreys_chain(8)
+    assert work["chained"] == n_windows - (-(-n_windows // 8))
+    assert not got["status"].any() and not plain["status"].any()
+    assert relerr(got["weights"], plain["weights"]) <= 1e-10 and relerr(got["w1"], plain["w1"]) <= 1e-10
+    for k in ("mu_g", "lambda_hat", "v_hat"):
+        i = SCAL_JORION[k]
+        assert np.max(np.abs(got["scalars"][:, i] - plain["scalars"][:, i]) / np.abs(plain["scalars"][:, i])) <= 1e-9, k
