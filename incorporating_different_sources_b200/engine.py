@@ -178,23 +178,8 @@ class BayesEngine:
         """Segment boundaries for a date-sorted conjugate batch: whole solver waves of windows per segment, so that
         every segment is solved at full occupancy while the next one is on the bus and less than one wave is left
         when the copy ends.  Returns cumulative row fractions for :meth:`set_upload_fractions`."""
-        wave = self.solve_wave_windows()
-        W = batch.n_windows
-        hi = np.asarray(batch.hf_hi, dtype=np.int64)
-        if W < 2 * wave or np.any(np.diff(hi) < 0):
-            return None
-        # whole waves per segment (several when there are more waves than segments), the remainder as the last one:
-        # a solver launch costs the latency of one factorisation however few windows it has, so short tail segments
-        # only add launches (measured: halving the remainder made the step 6 ms slower)
-        full = W // wave
-        per = -(-full // (max_segments - 1))
-        counts = [per * wave] * (full // per)
-        if full % per:
-            counts.append((full % per) * wave)
-        if W - full * wave > 0:
-            counts.append(W - full * wave)
-        ends = np.cumsum(counts)
-        return [float(hi[e - 1]) / float(n_hf_rows) for e in ends]
+        from .windows import plan_wave_fractions
+        return plan_wave_fractions(batch.hf_hi, n_hf_rows, self.solve_wave_windows(), max_segments)
 
     @property
     def launch_count(self) -> int:

@@ -114,6 +114,27 @@ def plan_daily_windows(spec, dates: np.ndarray, d_indices: Sequence[int], hf_ts:
     )
 
 
+def plan_wave_fractions(hf_hi: np.ndarray, n_hf_rows: int, wave: int, max_segments: int = 8):
+    """Cut points of a segmented intraday upload for a date-sorted conjugate batch (``bp_set_upload_fractions``):
+    whole solver waves of windows per segment (several per segment when there are more waves than segments), the
+    remainder as the last one.  A solver launch costs the latency of one factorisation however few windows it has, so
+    short tail segments only add launches (measured: halving the remainder made the step 6 ms slower).  Returns the
+    cumulative row fractions, or ``None`` when the batch is too small or not sorted by date."""
+    hi = np.asarray(hf_hi, dtype=np.int64)
+    W = int(hi.shape[0])
+    if wave <= 0 or W < 2 * wave or max_segments < 2 or np.any(np.diff(hi) < 0):
+        return None
+    full = W // wave
+    per = -(-full // (max_segments - 1))
+    counts = [per * wave] * (full // per)
+    if full % per:
+        counts.append((full % per) * wave)
+    if W - full * wave > 0:
+        counts.append(W - full * wave)
+    ends = np.cumsum(counts)
+    return [float(hi[e - 1]) / float(n_hf_rows) for e in ends]
+
+
 def trim_intraday(batch: WindowBatch):
     """Row range ``[lo, hi)`` of the intraday matrix that the windows of ``batch`` read; the batch is shifted in place
     so that it refers to ``hf_prices[lo:hi]``.  Bars outside the range (e.g. the years of history before the first

@@ -103,3 +103,31 @@ def test_partition_covers_every_window_once(world):
     for r in range(world):
         sh = make_shard(d_idx, 1008, r, world)
         assert sh.day_lo == sh.d_indices[0] - 1007 and sh.day_hi == sh.d_indices[-1] + 1
+
+
+def test_upload_segment_planner_and_intraday_trim():
+    """Pure host logic of the end-to-end pipeline: wave-aligned segment cuts and the intraday row range a batch reads."""
+    from incorporating_different_sources_b200.synthetic import generate_market
+    from incorporating_different_sources_b200.windows import plan_daily_windows, plan_wave_fractions, trim_intraday
+    mkt = generate_market(4, 400, seed=1, bars_per_day=6)
+    spec = dict(weighting_strategy="conjugate_hf_vix_vw", size=4, risk_aversion=5, rolling_window=100,
+                rolling_window_frequency="daily", mcm_scaling=1)
+    d_idx = list(range(150, 400))
+    b = plan_daily_windows(spec, mkt.dates, d_idx, mkt.hf_ts, hf_lookback_days=7)
+    R = mkt.hf_prices.shape[0]
+    fr = plan_wave_fractions(b.hf_hi, R, wave=60)
+    # 250 windows, waves of 60: 4 full waves + 10 windows -> 5 segments, each ending at the last bar of its last window
+    assert len(fr) == 5 and fr[-1] == 1.0 and all(x < y for x, y in zip(fr, fr[1:]))
+    assert [int(round(f * R)) for f in fr] == [int(b.hf_hi[k - 1]) for k in (60, 120, 180, 240, 250)]
+    # more waves than segments: several waves per segment, never more than max_segments
+    fr = plan_wave_fractions(b.hf_hi, R, wave=10, max_segments=8)
+    assert len(fr) <= 8 and fr[-1] == 1.0
+    assert plan_wave_fractions(b.hf_hi, R, wave=200) is None                       # less than two waves
+    assert plan_wave_fractions(b.hf_hi[::-1], R, wave=60) is None                  # not sorted by date
+    lo0, hi0 = b.hf_lo.copy(), b.hf_hi.copy()
+    lo, hi = trim_intraday(b)
+    assert lo == lo0.min() > 0 and hi == hi0.max() == R
+    assert np.array_equal(b.hf_lo + lo, lo0) and np.array_equal(b.hf_hi + lo, hi0) and b.hf_lo.min() == 0
+    # the trimmed rows are exactly the bars after (first trade date - 7 days + 1 day)
+    first = mkt.dates[d_idx[0]] - np.timedelta64(6, "D")
+    assert lo == int(np.searchsorted(mkt.hf_ts, first, side="right"))
