@@ -216,6 +216,23 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- our arm
+class _StdoutToStderr:
+    """NCCL prints its version banner on STDOUT when the communicator is created; the contract is ONE JSON line on
+    stdout, so file descriptor 1 points at stderr while the process group comes up."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def measure_dgemm_peak(torch, dev):
     n = 8192
     a = torch.randn(n, n, dtype=torch.float64, device=dev)
@@ -250,7 +267,11 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)                  # creates the communicator (and prints the banner) here
+            torch.cuda.synchronize()
     n_gpus = world
 
     peaks = {}
