@@ -1239,6 +1239,7 @@ int bp_destroy(bp_handle* h) {
     cudaFree(h->ws);
     cudaFree(h->stage);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     delete h;
     return BP_OK;
 }
