@@ -43,8 +43,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// 32 x 32 block of the factor at (row0, col0) -> dst[32][32]; rows >= N are zero-filled, on the diagonal (diag) the
-// missing rows become identity rows and the strictly upper part is cleared
+// 32 x 32 block of the factor at (row0, col0) -> dst[32][32]; rows >= N are zero-filled (the substitutions give those
+// rows a zero solution and never divide by their diagonal).  Only the lower triangle of a diagonal block is read.
 __device__ __forceinline__ void load_block_async(double* dst, const double* L, int ldS, int row0, int col0, int N, int tid) {
     // 256 threads x 2 chunks of 16 bytes: 32 rows x 16 chunks
 #pragma unroll
