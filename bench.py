@@ -616,8 +616,8 @@ def main():
     ap.add_argument("--n-assets", type=int, default=500)
     ap.add_argument("--windows", type=int, default=4150)
     ap.add_argument("--hf-days", type=int, default=7)
-    ap.add_argument("--cpu-sample", type=int, default=256)
-    ap.add_argument("--ref-sample", type=int, default=128)
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="windows of the in-run CPU baseline / parity check (~10 s)")
+    ap.add_argument("--ref-sample", type=int, default=1024, help="windows per step of the --impl reference arm (~2 s per step)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-widened", action="store_true", help="skip the Jorion / shrinkage measurements (SURVEY 8(f))")
     args = ap.parse_args()
