@@ -920,7 +920,9 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
     CU_TRY(cudaSetDevice(h->device));
     const Layout L = make_layout(h, B.max_m);
     int Wc = (int)std::min<size_t>((size_t)B.W, std::max<size_t>(1, h->ws_limit / L.per_window));
-    if (Wc < B.W) G = 0;
+    // (the descriptors were planned for the base windows only: the chain path must not be abandoned after upload_batch;
+    // the check above uses the same layout, so this cannot trigger unless the two are changed apart)
+    if (Wc < B.W && G >= 2) return fail(BP_ERR_STATE, "internal: chained batch does not fit one workspace chunk");
     // Pipelined against a segmented asynchronous intraday upload: prep + Gram of the windows whose bars have
     // arrived run while the rest is still being copied; the solve follows for all windows at once.
     const bool pipelined = mode == BP_MODE_CONJUGATE && h->hf_pending && h->n_seg > 1 && h->seg_waited < h->n_seg &&
