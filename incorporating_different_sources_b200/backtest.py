@@ -17,7 +17,7 @@ from typing import Callable, Dict, List, Optional
 import numpy as np
 import pandas as pd
 
-from .windows import HF_LOOKBACK_DAYS, ffill_rows, plan_daily_windows, plan_weekly_windows
+from .windows import HF_LOOKBACK_DAYS, ffill_rows, mcm_prior_n, plan_daily_windows, plan_weekly_windows
 
 # ``data_handling.extract_unique_tickers(d, d)`` of the reference reads the S&P-500 constituents of a date
 # from a CSV (:619); offline there is no such file, so the universe provider is pluggable.  Default: every
@@ -164,8 +164,14 @@ def _batched_weights(engine, portfolio_spec, market_data, dates_all, reb_pos, un
         raise NotImplementedError("monthly windows: resample('M') was removed from pandas (SURVEY F10)")
     rf_dates = rf_df.index.values.astype("datetime64[ns]")
     rf_vals = rf_df.iloc[:, 0].to_numpy(dtype=np.float64)
-    mcm = np.stack([market_data["vix_prices_df"].reindex(dates_all).iloc[:, 0].to_numpy(dtype=np.float64),
-                    market_data["epu_prices_df"].reindex(dates_all).iloc[:, 0].to_numpy(dtype=np.float64)])
+    # n0 per rebalance date from the MCM series' OWN calendar (7 observations a week for FRED's EPU index; the
+    # reference averages the last n observations whatever their dates, :95-112) -> injected as prior_n
+    prior_n_all = None
+    if conj:
+        mcm_df = market_data["vix_prices_df" if "vix" in strat else "epu_prices_df"]
+        prior_n_all = mcm_prior_n(portfolio_spec, mcm_df.index.values, mcm_df.iloc[:, 0].to_numpy(dtype=np.float64),
+                                  dates_ns[np.asarray(reb_pos, dtype=np.int64)])
+    mcm = None
     for idx, rows in groups.items():
         cols = list(idx)
         engine.upload_market(prices=prices_df.to_numpy(dtype=np.float64)[:, cols], rf_row=rf_row,
@@ -177,13 +183,15 @@ def _batched_weights(engine, portfolio_spec, market_data, dates_all, reb_pos, un
             spec = dict(portfolio_spec, weighting_strategy="conjugate_hf_vix_" + strat, mcm_scaling=1,
                         rolling_window=3, rolling_window_frequency="daily", risk_aversion=1)
             batch = plan_daily_windows(spec, dates_ns, d_idx, hf_ts)
+            batch.prior_n = np.ones(len(d_idx))                 # w0 does not depend on the MCM series
             w = engine.moments(batch, outputs=("w0",))["w0"]
         elif conj:
             if weekly:
-                rows_w, batch = plan_weekly_windows(portfolio_spec, dates_ns, d_idx, rf_dates, rf_vals, mcm, hf_ts)
+                rows_w, batch = plan_weekly_windows(portfolio_spec, dates_ns, d_idx, rf_dates, rf_vals, None, hf_ts)
                 engine.set_resampled(rows_w)
             else:
                 batch = plan_daily_windows(portfolio_spec, dates_ns, d_idx, hf_ts)
+            batch.prior_n = np.ascontiguousarray(prior_n_all[rows])
             res = engine.conjugate(batch, outputs=("weights", "status"))
             _raise_on_status(res["status"], dates_all, d_idx)
             w = res["weights"]

@@ -903,6 +903,10 @@ int finish(bp_handle* h) {
 // shared driver of bp_conjugate_batched / bp_jeffreys_batched / bp_stats_batched / bp_hf_cov_batched
 int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, int mode, bool solve, int estimator = BP_EST_NONE) {
     Batch B;
+    if (!h || !b) return fail(BP_ERR_INVALID, "null handle or batch");
+    // every allocation / launch below (upload_batch included) must land on the handle's device, whatever the
+    // calling thread's current device is (two handles on two GPUs in one thread, or torch having switched)
+    CU_TRY(cudaSetDevice(h->device));
     // Jeffreys batches of consecutive trade dates: factorise every G-th window only (jeffreys_chain.cu)
     int G = 0;
     if (h && b && out && mode == BP_MODE_JEFFREYS && (estimator == BP_EST_NONE || estimator == BP_EST_JORION) && solve && !out->T && !out->S0 && !out->S1 &&
@@ -912,12 +916,16 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
         for (int w = 1; consecutive && w < b->n_windows; ++w) consecutive = b->day_row[w] == b->day_row[0] + w;
         const Layout L0 = make_layout(h, 0);
         if (consecutive && (size_t)b->n_windows * L0.per_window <= h->ws_limit) G = std::min(h->chain_group, chain_max_group());
+        // Conditioning guard: window b+k is the base with k rows removed and k rows added; the down-dated matrix
+        // has rank n-1-k, and its Woodbury pivots -1 + l'J_b^-1 l tend to 0 as n-1-k approaches N (leverage 1),
+        // where the small system loses digits while no pivot is exactly zero.  Chain only with a margin of rows;
+        // closer to the rank limit every window is factorised on its own (the path the parity tests pin).
+        if (G >= 2 && b->rolling_window - 1 < h->N + 2 * G + 8) G = 0;
     }
     if (h) h->work_stride = G >= 2 ? G : 1;
     int rc = upload_batch(h, b, mode == BP_MODE_CONJUGATE, &B);
     if (h) h->work_stride = 1;
     if (rc) return rc;
-    CU_TRY(cudaSetDevice(h->device));
     const Layout L = make_layout(h, B.max_m);
     int Wc = (int)std::min<size_t>((size_t)B.W, std::max<size_t>(1, h->ws_limit / L.per_window));
     // (the descriptors were planned for the base windows only: the chain path must not be abandoned after upload_batch;
@@ -1248,7 +1256,14 @@ int bp_destroy(bp_handle* h) {
 
 int bp_set_stream(bp_handle* h, void* cuda_stream) {
     if (!h) return fail(BP_ERR_INVALID, "null handle");
-    h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if (st != h->stream) {
+        // work queued on the old stream still uses the shared workspace, staging buffer and descriptor slots
+        CU_TRY(cudaSetDevice(h->device));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        h->need_sync = false;
+        h->stream = st;
+    }
     return BP_OK;
 }
 
@@ -1661,9 +1676,9 @@ int bp_excess_returns(bp_handle* h, const bp_window_batch* b, double* X) {
     if (!h || !b || !X) return fail(BP_ERR_INVALID, "null argument");
     if (b->n_windows != 1) return fail(BP_ERR_INVALID, "bp_excess_returns handles one window per call");
     Batch B;
+    CU_TRY(cudaSetDevice(h->device));
     int rc = upload_batch(h, b, false, &B);
     if (rc) return rc;
-    CU_TRY(cudaSetDevice(h->device));
     const int K = b->rolling_window - 1;
     const size_t bytes = sizeof(double) * (size_t)K * h->N;
     const bool dev = is_device_ptr(X);

@@ -66,14 +66,22 @@ __global__ void __launch_bounds__(LOOP_THREADS) backtest_loop_kernel(LoopParams 
     }
     if (s == 0) return;                       // the first rebalance has no preceding segment
 
-    // ---- segment: days reb_row[s-1]+1 .. reb_row[s], starting from the weights chosen at rebalance s-1
+    // ---- segment: days reb_row[s-1]+1 .. reb_row[s], starting from the weights chosen at rebalance s-1.
+    // Only the stocks HELD since rebalance s-1 take part (the reference reindexes the day's returns to the
+    // portfolio's own index, :1134); columns outside that universe may hold NaN prices (before listing, after
+    // delisting) and are never read.  A held stock whose return is NaN drops out of every sum exactly as pandas'
+    // skipna sums drop it (:1137, :1143, :1156): its weight becomes NaN and stays NaN for the rest of the segment,
+    // and the turnover's outer merge + fillna(0) (:1057-1064) counts it as 0.
     const double* w_old_ptr = p.weights + (long long)(s - 1) * p.ldw;
+    const unsigned char* held_ptr = p.member ? p.member + (long long)(s - 1) * N : nullptr;
     constexpr int PER = 8;                    // assets per thread (N <= 2048)
     double w[PER];
+    bool held[PER];
 #pragma unroll
     for (int e = 0; e < PER; ++e) {
         const int i = tid + e * LOOP_THREADS;
-        w[e] = i < N ? w_old_ptr[i] : 0.0;
+        held[e] = i < N && (held_ptr == nullptr || held_ptr[i] != 0);
+        w[e] = held[e] ? w_old_ptr[i] : 0.0;
     }
     for (int d = p.reb_row[s - 1] + 1; d <= d_reb; ++d) {
         double pr = 0.0, sw = 0.0;
@@ -82,13 +90,14 @@ __global__ void __launch_bounds__(LOOP_THREADS) backtest_loop_kernel(LoopParams 
         for (int e = 0; e < PER; ++e) {
             const int i = tid + e * LOOP_THREADS;
             ret[e] = 0.0;
-            if (i < N) {
+            if (held[e]) {
                 ret[e] = p.prices[(long long)d * p.ld_prices + i] / p.prices[(long long)(d - 1) * p.ld_prices + i] - 1.0;  // pct_change
-                pr = fma(ret[e], w[e], pr);
-                sw += w[e];
+                const double prod = ret[e] * w[e];
+                if (!isnan(prod)) pr += prod;                          // Series.sum() skips NaN (:1137)
+                if (!isnan(w[e])) sw += w[e];
             }
         }
-        pr = block_sum(pr, scratch);                                   // :1137
+        pr = block_sum(pr, scratch);
         sw = block_sum(sw, scratch);
         const double rf_d = pow(p.rf_row[d] + 1.0, 1.0 / 252.0) - 1.0;  // :1142
         double r = pr + (1.0 - sw) * rf_d;                             // :1143
@@ -96,23 +105,30 @@ __global__ void __launch_bounds__(LOOP_THREADS) backtest_loop_kernel(LoopParams 
         double sw2 = 0.0;
 #pragma unroll
         for (int e = 0; e < PER; ++e) {
-            w[e] = w[e] * (1.0 + ret[e]);                              // :1152-1153
-            sw2 += w[e];
+            if (held[e]) {
+                w[e] = w[e] * (1.0 + ret[e]);                          // :1152-1153
+                if (!isnan(w[e])) sw2 += w[e];
+            }
         }
         sw2 = block_sum(sw2, scratch);
         const double total = sw2 + upd_rf;                             // :1156
 #pragma unroll
         for (int e = 0; e < PER; ++e) w[e] = w[e] / total;             // :1159
         if (d == d_reb && !tail) {
-            // turnover against the new weights (:1054-1075) and transaction cost (:1214-1215)
+            // turnover against the new weights (:1054-1075) and transaction cost (:1214-1215): outer merge of
+            // the two index sets, missing / NaN entries count as 0
+            const unsigned char* new_ptr = p.member ? p.member + (long long)s * N : nullptr;
             double diff = 0.0, sb = 0.0, sa = 0.0;
 #pragma unroll
             for (int e = 0; e < PER; ++e) {
                 const int i = tid + e * LOOP_THREADS;
                 if (i < N) {
-                    const double wa = w_new_ptr[i];
-                    diff += fabs(w[e] - wa);
-                    sb += w[e];
+                    const bool in_new = new_ptr == nullptr || new_ptr[i] != 0;
+                    const double wa_raw = in_new ? w_new_ptr[i] : 0.0;
+                    const double wa = isnan(wa_raw) ? 0.0 : wa_raw;
+                    const double wb = (held[e] && !isnan(w[e])) ? w[e] : 0.0;
+                    diff += fabs(wb - wa);
+                    sb += wb;
                     sa += wa;
                 }
             }

@@ -224,6 +224,57 @@ def plan_weekly_windows(spec, dates: np.ndarray, d_indices: Sequence[int], rf_da
     return rows, batch
 
 
+def mcm_prior_n(spec, mcm_dates: np.ndarray, mcm_values: np.ndarray, trade_dates: np.ndarray) -> np.ndarray:
+    """``calculate_conjugate_prior_n`` (:247-267) for many trade dates, on the MCM series' OWN calendar.
+
+    The reference averages the last ``rolling_window`` observations of the MCM frame it is handed (rows <= d, :977-983),
+    whatever their dates are — FRED's daily EPU index has 7 observations per week, VIX has 5 — and for weekly windows
+    the last observation of every ``resample('W')`` bucket (:106), the bucket of d ending at d itself.  Empty buckets
+    are NaN rows that ``iloc[-n:]`` counts and ``mean()`` skips.  A trade date missing from the MCM index raises the
+    reference's ``ValueError`` (:98-100).  Returns ``n0`` [W], to be passed as ``WindowBatch.prior_n``."""
+    n = int(spec["rolling_window"])
+    freq = spec["rolling_window_frequency"]
+    s = float(spec["mcm_scaling"])
+    md = np.asarray(mcm_dates).astype("datetime64[ns]")
+    mv = np.asarray(mcm_values, dtype=np.float64)
+    order = np.argsort(md, kind="stable")                                   # sort_index() (:95)
+    md, mv = md[order], mv[order]
+    td = np.asarray(trade_dates).astype("datetime64[ns]")
+    pos = np.searchsorted(md, td, side="right") - 1                          # last observation <= d
+    bad = (pos < 0) | (md[np.maximum(pos, 0)] != td)
+    if bad.any():
+        d = td[np.nonzero(bad)[0][0]]
+        raise ValueError(f"trading_date_ts {d} must be the last date in the DataFrame.")   # :98-100
+    cur = mv[pos]                                                           # mcm_prices_df.loc[d] (:257)
+    avg = np.empty(len(td))
+    if freq == "daily":
+        for i, p in enumerate(pos):
+            avg[i] = np.nanmean(mv[max(0, p - n + 1): p + 1])              # iloc[-n:].mean() (:112)
+    elif freq == "weekly":
+        wid = week_ids(md)
+        w0 = int(wid[0])
+        n_weeks = int(wid[-1]) - w0 + 1
+        week_last = np.full(n_weeks, np.nan)
+        ok = ~np.isnan(mv)
+        week_last[wid[ok] - w0] = mv[ok]                                    # last() = last non-NaN; ascending dates: the last write wins
+        for i, p in enumerate(pos):
+            k = int(wid[p]) - w0                                            # bucket of d ends at d (the frame is cut at d)
+            j, own = int(p), np.nan
+            while j >= 0 and wid[j] == wid[p]:
+                if ok[j]:
+                    own = mv[j]
+                    break
+                j -= 1
+            vals = np.r_[week_last[max(0, k - n + 1): k], own]
+            avg[i] = np.nanmean(vals)
+    elif freq == "monthly":
+        raise NotImplementedError("monthly windows: resample('M') was removed from pandas (SURVEY F10)")
+    else:
+        raise RuntimeError("Unknown rolling window frequency.")
+    frac = np.where(cur > avg, cur / avg, avg / cur)                         # :260-263
+    return n * frac * s                                                      # :265
+
+
 def ffill_rows(target_dates: np.ndarray, src_dates: np.ndarray, src_values: np.ndarray) -> np.ndarray:
     """``series.reindex(target, method='ffill')`` (:54) for sorted date arrays."""
     idx = np.searchsorted(src_dates, target_dates, side="right") - 1

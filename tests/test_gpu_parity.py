@@ -391,6 +391,28 @@ def test_gpu_jeffreys_chain_matches_oracle_and_per_window_path(engine, n_assets,
         assert relerr(got["weights"][i], ref) <= TOL, f"window {i}"
 
 
+def test_gpu_jeffreys_chain_guard_near_rank_limit(engine):
+    """n - 1 close to N: the down-dated matrices of a chain group approach rank deficiency (leverage -> 1) and the
+    Woodbury pivots lose digits without ever being exactly zero, so such batches are NOT chained
+    (rolling_window - 1 < N + 2*group + 8): every window takes the per-window factorisation the parity is pinned on."""
+    from incorporating_different_sources_b200.engine import upload_synthetic
+    from incorporating_different_sources_b200.synthetic import generate_market
+    from incorporating_different_sources_b200.windows import plan_daily_windows
+    N, n, W = 60, 80, 40
+    mkt = generate_market(N, n + W + 3, seed=8177, bars_per_day=2)
+    spec = dict(weighting_strategy="jeffreys", size=N, risk_aversion=3, turnover_cost=15, rebalancing_frequency="daily",
+                rolling_window=n, rolling_window_frequency="daily", mcm_scaling=None, display_name="x")
+    d_idx = list(range(n + 3, n + W + 3))
+    upload_synthetic(engine, mkt)
+    engine.solve_work()
+    got = engine.jeffreys(plan_daily_windows(spec, mkt.dates, d_idx, need_hf=False), outputs=("weights", "status"))
+    assert engine.solve_work() == {"factored": float(W), "chained": 0.0}
+    assert not got["status"].any()
+    for i in (0, 9, W - 1):
+        ref = bo.jeffreys_window(spec, mkt, d_idx[i], np.arange(N))["weights"]
+        assert relerr(got["weights"][i], ref) <= TOL, f"window {i}"
+
+
 def test_gpu_jeffreys_chain_only_for_consecutive_dates(engine):
     """Every other date: not consecutive -> per-window path (no window is chained), results still match the oracle."""
     from incorporating_different_sources_b200.engine import upload_synthetic

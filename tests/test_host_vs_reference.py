@@ -103,3 +103,26 @@ def test_rebalance_calendar_matches_reference_loop():
         assert list(bt.rebalance_flags(days, freq)) == ref
     with pytest.raises(ValueError):
         bt.rebalance_flags(days, "yearly")
+
+
+@pytest.mark.parametrize("freq", ["daily", "weekly"])
+def test_mcm_prior_n_on_the_series_own_calendar_matches_reference(freq):
+    """FRED's daily EPU index has an observation on every CALENDAR day: the reference averages the last n
+    observations (daily) / the last n weekly buckets (weekly, Sunday's value) of that calendar (:95-112), not the
+    last n trading days.  NaN observations and a missing trade date behave like the reference."""
+    from incorporating_different_sources_b200.windows import mcm_prior_n
+    pc = load_reference(check=True)
+    rng = np.random.default_rng(11)
+    cal = pd.date_range("2009-01-01", periods=900, freq="D")
+    epu = pd.DataFrame({"EPU": 100.0 * np.exp(0.3 * rng.standard_normal(len(cal)))}, index=cal)
+    epu.iloc[[100, 101, 350, 357, 500, 506, 520, 560], 0] = np.nan          # holes inside the windows, Sundays among them
+    trade = pd.bdate_range("2010-06-01", periods=120)
+    trade = trade[~np.isnan(epu.loc[trade, "EPU"].to_numpy())]
+    spec = dict(rolling_window=60 if freq == "daily" else 30, rolling_window_frequency=freq, mcm_scaling=1.7,
+                weighting_strategy="conjugate_hf_epu_vw")
+    got = mcm_prior_n(spec, epu.index.values, epu["EPU"].to_numpy(), trade.values)
+    for i, d in enumerate(trade):
+        ref = pc.calculate_conjugate_prior_n(spec, d, epu.loc[epu.index <= d])
+        assert abs(got[i] - ref) <= 1e-13 * abs(ref), (freq, d, got[i], ref)
+    with pytest.raises(ValueError):
+        mcm_prior_n(spec, epu.index.values[::2], epu["EPU"].to_numpy()[::2], trade.values)
