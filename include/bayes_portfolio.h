@@ -154,6 +154,14 @@ int bp_get_gram_work(bp_handle* h, double* out4);
 /* Smallest batch (windows) for which the Gram kernel reuses precomputed block tiles between overlapping
  * windows; INT_MAX disables the reuse (every window is contracted from scratch). Default 32. */
 int bp_set_reuse_min_windows(bp_handle* h, int min_windows);
+/* Long intraday look-backs (the 252-day HF window of BASELINE config 3, reached in the reference through
+ * conjugate_prior_S_df=, :299-318): the look-back of every window covers whole trading days, so the bars are cut into day
+ * blocks at the hf_lo / hf_hi values of the batch, each block's Gram tile is contracted once, and for windows of at
+ * least `min_days` blocks the tiles are scanned per chunk (suffix / prefix sums, no subtraction) so that a window adds
+ * at most THREE stored tiles whatever its look-back; its column means come from the scanned per-day sums and S0 w0
+ * from a by-product of the Gram launch, so no kernel walks the window's own rows.  0 disables (one tile per day).
+ * Default 8. */
+int bp_set_hf_presum_min_days(bp_handle* h, int min_days);
 /* Jeffreys batches of CONSECUTIVE trade dates (calculate_mean_jeffreys_posterior_nu, :580-608): consecutive windows
  * differ by a rank 2k+4 term (k rows in, k rows out, the change of the risk-free adjustment and of t t'/n), so only
  * every `group`-th window is factorised and the others are solved relative to it by the Woodbury identity (30

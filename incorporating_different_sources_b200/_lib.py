@@ -28,7 +28,7 @@ EXPORTED = [
     "bp_excess_returns", "bp_quadratic_form", "bp_dense_posterior", "bp_moments_batched",
     "bp_upload_market_async", "bp_backtest_batched", "bp_get_gram_work", "bp_set_reuse_min_windows", "bp_set_upload_pipeline", "bp_set_async_outputs",
     "bp_set_resampled", "bp_estimator_batched", "bp_set_jeffreys_chain", "bp_get_solve_work",
-    "bp_set_upload_fractions", "bp_solve_wave_windows",
+    "bp_set_upload_fractions", "bp_solve_wave_windows", "bp_set_hf_presum_min_days",
 ]
 BP_NSTAGE = 8
 STAGES = ("logret", "prep", "gram", "solve", "chain")
@@ -127,6 +127,7 @@ def load():
     lib.bp_set_resampled.argtypes = [C.c_void_p, C.POINTER(ResampledDesc)]
     lib.bp_get_gram_work.argtypes = [C.c_void_p, c_double_p]
     lib.bp_set_reuse_min_windows.argtypes = [C.c_void_p, C.c_int]
+    lib.bp_set_hf_presum_min_days.argtypes = [C.c_void_p, C.c_int]
     lib.bp_set_upload_fractions.argtypes = [C.c_void_p, C.c_int, c_double_p]
     lib.bp_solve_wave_windows.argtypes = [C.c_void_p]
     lib.bp_set_jeffreys_chain.argtypes = [C.c_void_p, C.c_int]

@@ -115,6 +115,12 @@ struct bp_handle {
     double* fstore = nullptr;                                            // phase-B combined runs (coarse + fine + fine)
     size_t fstore_cap = 0;
     int reuse_min_windows = 32;
+    // pre-summed intraday day blocks (long HF look-backs): windows with at least this many trading days add <= 3 scanned
+    // tiles instead of one tile per day (0 disables); vector store [3 nb][ld] of the scanned per-day column sums
+    int presum_min_days = 8;
+    double* vstore = nullptr;
+    size_t vstore_cap = 0;
+    double work_scan_tiles = 0;
     // work counters of the Gram stage since the last bp_get_gram_work (bench.py's roofline accounting)
     double work_k_rows = 0, work_add_blocks = 0, work_pre_rows = 0, work_full_rows = 0;
     // Jeffreys windows of consecutive trade dates: only every chain_group-th window is factorised, the others are
@@ -253,17 +259,18 @@ int ensure_stage(bp_handle* h, size_t bytes) {
 
 struct Chunk {
     // carved from the workspace for Wc windows
-    double *S, *t, *pvec, *gvec, *rhs, *w0, *s0w0, *w1, *nu, *weights, *scal, *y;
+    double *S, *t, *pvec, *gvec, *rhs, *w0, *s0w0, *w1, *nu, *weights, *scal, *y, *mv;
     int* status;
 };
 
 struct Layout {
     int N, ldv, ldS, rowsS;
-    long long win_stride, y_stride;
+    long long win_stride, y_stride, mv_stride;
     size_t per_window;
 };
 
-Layout make_layout(const bp_handle* h, int max_m) {
+// max_m: longest intraday window (scratch of the row dots); with_mv: room for the Gram kernel's G w0 partials
+Layout make_layout(const bp_handle* h, int max_m, bool with_mv = false) {
     Layout L;
     L.N = h->N;
     L.ldv = h->ld;
@@ -271,7 +278,9 @@ Layout make_layout(const bp_handle* h, int max_m) {
     L.rowsS = L.ldS + 8;
     L.win_stride = (long long)L.rowsS * L.ldS;
     L.y_stride = round_up(std::max(max_m, 2), 2);
-    L.per_window = sizeof(double) * ((size_t)L.win_stride + 9 * (size_t)L.ldv + BP_NSCAL + (size_t)L.y_stride) + 16;
+    const int nt = (h->N + GRAM_TILE - 1) / GRAM_TILE;
+    L.mv_stride = with_mv ? (long long)(nt * (nt + 1) / 2) * 2 * GRAM_TILE : 0;
+    L.per_window = sizeof(double) * ((size_t)L.win_stride + 9 * (size_t)L.ldv + BP_NSCAL + (size_t)L.y_stride + (size_t)L.mv_stride) + 16;
     return L;
 }
 
@@ -290,6 +299,7 @@ Chunk carve(unsigned char* ws, const Layout& L, int Wc) {
     c.weights = p;  p += (size_t)Wc * L.ldv;
     c.scal = p;     p += (size_t)Wc * BP_NSCAL;
     c.y = p;        p += (size_t)Wc * L.y_stride;
+    c.mv = p;       p += (size_t)Wc * L.mv_stride;
     c.status = reinterpret_cast<int*>(p);
     return c;
 }
@@ -303,6 +313,7 @@ Chunk chunk_at(const Chunk& c, const Layout& L, int k) {
     o.w1 += (size_t)k * L.ldv;      o.nu += (size_t)k * L.ldv;    o.weights += (size_t)k * L.ldv;
     o.scal += (size_t)k * BP_NSCAL;
     o.y += (size_t)k * L.y_stride;
+    o.mv += (size_t)k * L.mv_stride;
     o.status += k;
     return o;
 }
@@ -326,8 +337,13 @@ struct Batch {
     bool band_ok = false;              // consecutive trade dates: the daily pass runs as a banded GEMM
     // intraday block grid (for the pipelined upload): block k of level l ends at return row hf_off + (hf_bmin[l]+k+1)*hf_blk[l]
     int hf_off = 0, hf_bmin[2] = {0, 0}, hf_blk[2] = {0, 0};
-    bool hf_inner = false;             // inner day blocks + gathered overnight rows (see PhasePlan::inner)
+    bool hf_inner = false;             // day blocks without their overnight return + gathered overnight rows (PhasePlan::inner)
     int hf_nb0 = 0;
+    std::vector<int> hf_starts;        // inner: price row where day block k starts (nb + 1 entries), host copy
+    const int* hf_starts_dev = nullptr;
+    bool presum = false;               // windows add <= 3 scanned tiles (PhasePlan::chunk)
+    int presum_chunk = 0;
+    const int* hf_vids = nullptr;      // [W][3] scanned-vector ids of each window
 };
 
 // Block grids of one phase, two levels (0 = coarse, 1 = fine; the fine size divides the coarse size): block b of
@@ -336,10 +352,14 @@ struct PhasePlan {
     int blk[2] = {0, 0};
     int off = 0;
     int bmin[2] = {0, 0}, nb[2] = {0, 0};
-    // "inner" blocks (regular intraday calendar): block b is rows off + b*blk + 1 .. off + (b+1)*blk - 1, i.e. a
-    // trading day WITHOUT its first (overnight) return; the overnight rows are gathered into a compact row range
-    // behind the intraday matrix, so a window is [its days' inner blocks] + [one short run of overnight rows]
+    // "inner" day blocks: every hf_lo / hf_hi of the batch is a block boundary (the HF look-back always covers whole
+    // days, :310-312, whatever the bar calendar), block b = return rows starts[b]+1 .. starts[b+1]-1, i.e. a trading
+    // day WITHOUT its first (overnight) return; the overnight rows are gathered into a compact row range behind the
+    // intraday matrix, so a window is [its days' inner blocks] + [one short run of overnight rows]
     bool inner = false;
+    std::vector<int> starts;
+    // pre-summed runs (long look-backs): chunk > 0 -> a window adds suffix'[first day] + prefix[...] tiles (<= 3)
+    int chunk = 0;
 };
 
 inline long long floor_div(long long a, long long b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
@@ -440,21 +460,60 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             else if (K >= 128) { plan[1].blk[0] = 64; plan[1].blk[1] = 16; }
         }
         if (need_hf) {
-            // regular intraday calendar: every window has the same number of rows and consecutive windows
-            // advance by a constant stride that divides it -> one block per stride (a trading day of bars)
-            const int H0 = b->hf_hi[0] - b->hf_lo[0];
-            int stride = W > 1 ? b->hf_lo[1] - b->hf_lo[0] : 0;
-            bool regular = stride > 0 && H0 % stride == 0 && H0 >= 2 * stride;
-            for (int w = 0; regular && w < W; ++w)
-                regular = b->hf_hi[w] - b->hf_lo[w] == H0 && (b->hf_lo[w] - b->hf_lo[0]) % stride == 0;
-            if (regular) {
-                plan[0].blk[0] = stride;
-                plan[0].off = b->hf_lo[0] % stride;
-                static const bool no_inner = getenv("BP_NO_INNER_BLOCKS") != nullptr;
-                plan[0].inner = !no_inner && stride >= 8;
-            } else if (H0 >= 3 * 64) {
-                plan[0].blk[0] = 64;
-                plan[0].blk[1] = 16;
+            // Day blocks: the HF look-back of every window covers whole days, so the sorted set of all hf_lo / hf_hi
+            // values cuts the bars into blocks of which every window is a run -- whatever the bar calendar (half
+            // days, holidays).  Worth it when the windows overlap (each block serves >= 2 windows on average).
+            static const bool no_inner = getenv("BP_NO_INNER_BLOCKS") != nullptr;
+            std::vector<int>& st = plan[0].starts;
+            st.reserve(2 * (size_t)W);
+            for (int w = 0; w < W; ++w) { st.push_back(b->hf_lo[w]); st.push_back(b->hf_hi[w]); }
+            std::sort(st.begin(), st.end());
+            st.erase(std::unique(st.begin(), st.end()), st.end());
+            if (st.size() >= 3) {
+                // stretches no window starts or ends in (the look-back of the first windows of a short batch) would be
+                // single giant blocks contracted by one CTA per tile pair: cut them to the typical block length (a
+                // window contains such a stretch entirely or not at all, so any cut inside it is a valid boundary)
+                std::vector<int> gaps(st.size() - 1);
+                for (size_t k = 0; k + 1 < st.size(); ++k) gaps[k] = st[k + 1] - st[k];
+                std::nth_element(gaps.begin(), gaps.begin() + gaps.size() / 2, gaps.end());
+                const int typical = std::max(8, gaps[gaps.size() / 2]);
+                std::vector<int> cut;
+                cut.reserve(st.size());
+                for (size_t k = 0; k + 1 < st.size(); ++k) {
+                    cut.push_back(st[k]);
+                    const int gap = st[k + 1] - st[k];
+                    if (gap > 2 * typical) {
+                        const int pieces = gap / typical;
+                        for (int q = 1; q < pieces; ++q) cut.push_back(st[k] + (int)((long long)gap * q / pieces));
+                    }
+                }
+                cut.push_back(st.back());
+                st.swap(cut);
+            }
+            const long long nb = (long long)st.size() - 1;
+            long long sumD = 0;
+            int minD = 1 << 30, maxD = 0, min_rows = 1 << 30;
+            for (int w = 0; w < W; ++w) {
+                const int D = (int)(std::lower_bound(st.begin(), st.end(), b->hf_hi[w]) - std::lower_bound(st.begin(), st.end(), b->hf_lo[w]));
+                sumD += D; minD = std::min(minD, D); maxD = std::max(maxD, D);
+            }
+            for (long long k = 0; k < nb; ++k) min_rows = std::min(min_rows, st[k + 1] - st[k]);
+            const bool day_blocks = !no_inner && nb >= 2 && minD >= 2 && min_rows >= 8 && sumD >= 2 * nb && nb <= h->hf_extra_rows;
+            if (day_blocks) {
+                plan[0].inner = true;
+                plan[0].blk[0] = 1;                 // level 0 in use (block sizes vary: see starts)
+                const int minL = minD - 1, maxL = maxD - 1;       // full days (overnight return included) per window
+                static const bool no_presum = getenv("BP_NO_PRESUM") != nullptr;
+                if (!no_presum && h->presum_min_days > 0 && minD >= h->presum_min_days && maxL <= 2 * minL &&
+                    3 * (size_t)nb * npairs_t * GRAM_BLOCK_TILE_DOUBLES * sizeof(double) <= h->ws_limit)
+                    plan[0].chunk = minL;
+            } else {
+                st.clear();
+                const int H0 = b->hf_hi[0] - b->hf_lo[0];
+                if (H0 >= 3 * 64) {
+                    plan[0].blk[0] = 64;
+                    plan[0].blk[1] = 16;
+                }
             }
         }
     }
@@ -467,9 +526,10 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         int row0, rows;
         phase_rows(ph, w, row0, rows);
         if (ph == 0 && plan[0].inner) {
+            const std::vector<int>& st = plan[0].starts;
             Split sp;
-            sp.c_lo = (b->hf_lo[w] - plan[0].off) / plan[0].blk[0];
-            sp.c_hi = sp.c_lo + (b->hf_hi[w] - b->hf_lo[w]) / plan[0].blk[0];
+            sp.c_lo = std::lower_bound(st.begin(), st.end(), b->hf_lo[w]) - st.begin();
+            sp.c_hi = std::lower_bound(st.begin(), st.end(), b->hf_hi[w]) - st.begin();
             return sp;
         }
         return split_rows(row0, rows, plan[ph]);
@@ -503,11 +563,12 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             if (hi[l] <= lo[l]) { plan[ph].blk[l] = 0; plan[ph].nb[l] = 0; continue; }
             plan[ph].bmin[l] = (int)lo[l];
             plan[ph].nb[l] = (int)(hi[l] - lo[l]);
-            const size_t need = (size_t)plan[ph].nb[l] * npairs_t * GRAM_BLOCK_TILE_DOUBLES;
+            size_t need = (size_t)plan[ph].nb[l] * npairs_t * GRAM_BLOCK_TILE_DOUBLES;
             if (need * sizeof(double) > h->ws_limit / 2) {      // too big: give up the reuse of this phase
                 plan[ph] = PhasePlan();
                 break;
             }
+            if (ph == 0 && l == 0 && plan[0].chunk > 0) need *= 3;      // + suffix' and prefix tiles of every block
             if (need > h->store_cap[ph][l]) {
                 CU_TRY(cudaStreamSynchronize(h->stream));
                 cudaFree(h->store[ph][l]);
@@ -518,17 +579,19 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             }
         }
     }
-    if (plan[0].inner && (plan[0].nb[0] <= 0 || (long long)plan[0].nb[0] > h->hf_extra_rows)) {
-        // no room for the overnight rows behind the intraday matrix (or the reuse was given up): plain day blocks
-        plan[0].inner = false;
-        if (plan[0].blk[0] > 0) {
-            long long lo = 1LL << 40, hi = -(1LL << 40);
-            for (int w = 0; w < W; ++w) {
-                const Split sp = split_of(0, w);
-                if (sp.c_hi > sp.c_lo) { lo = std::min(lo, sp.c_lo); hi = std::max(hi, sp.c_hi); }
-            }
-            if (hi > lo) { plan[0].bmin[0] = (int)lo; plan[0].nb[0] = (int)(hi - lo); }
-            else { plan[0].blk[0] = 0; plan[0].nb[0] = 0; }
+    if (plan[0].inner && plan[0].nb[0] != (int)plan[0].starts.size() - 1)
+        return fail(BP_ERR_STATE, "internal: day-block plan out of step with its boundaries");
+    const bool presum = plan[0].inner && plan[0].chunk > 0;
+    const int nb0 = plan[0].inner ? plan[0].nb[0] : 0;
+    if (presum) {
+        const size_t need = 3 * (size_t)nb0 * h->ld;
+        if (need > h->vstore_cap) {
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            cudaFree(h->vstore);
+            h->vstore = nullptr;
+            h->vstore_cap = 0;
+            CU_TRY(cudaMalloc(&h->vstore, need * sizeof(double)));
+            h->vstore_cap = need;
         }
     }
     int nranges[2] = {0, 0};
@@ -561,7 +624,8 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
     }
     const int nb_total = plan[0].nb[0] + plan[0].nb[1] + plan[1].nb[0] + plan[1].nb[1];
     const size_t ints_needed = (size_t)(7 + GRAM_DESC_INTS) * W + (size_t)GRAM_DESC_INTS * nb_total +
-                               2 * (size_t)(nranges[0] + nranges[1]) + 3 * (size_t)nfull;
+                               2 * (size_t)(nranges[0] + nranges[1]) + 3 * (size_t)nfull +
+                               (plan[0].inner ? (size_t)nb0 + 1 : 0) + (presum ? 3 * (size_t)W : 0);
     const int slot = h->desc_turn ^= 1;
     if (h->ev_desc_armed[slot]) {
         CU_TRY(cudaEventSynchronize(h->ev_desc[slot]));      // its staging buffer has been fetched
@@ -619,7 +683,24 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
             max_m = std::max(max_m, m);
             int* dA = gd + (size_t)w * GRAM_DESC_INTS;
             write_phase_desc(split_of(0, w), plan[0], dA);
-            if (plan[0].inner) {
+            if (presum) {
+                // suffix'[first day] (+ one whole chunk) (+ prefix[last day]): explicit tile ids into the unified store
+                // [inner | suffix' | prefix]; the same ids address the scanned column sums (hf_vids)
+                const int C = plan[0].chunk, c_lo = dA[4], last = dA[4] + dA[5] - 1;
+                const int qa = c_lo / C, s_next = std::min((qa + 1) * C, nb0);
+                int ids[3] = {nb0 + c_lo, -1, -1};
+                if (s_next <= last) {
+                    const int ql = last / C;
+                    if (ql > qa + 2) return fail(BP_ERR_STATE, "internal: pre-summed run spans more than three chunks");
+                    if (ql == qa + 2) ids[1] = 2 * nb0 + (qa + 2) * C - 1;
+                    ids[2] = 2 * nb0 + last;
+                }
+                dA[0] = dA[1] = dA[2] = dA[3] = 0;
+                for (int k = 0; k < 3; ++k) { dA[4 + 2 * k] = ids[k] >= 0 ? ids[k] : 0; dA[5 + 2 * k] = ids[k] >= 0 ? 1 : 0; }
+                int* vid = host + ((size_t)(7 + GRAM_DESC_INTS) * W + (size_t)GRAM_DESC_INTS * nb_total +
+                                   2 * (size_t)(nranges[0] + nranges[1]) + 3 * (size_t)nfull + (size_t)nb0 + 1) + 3 * (size_t)w;
+                vid[0] = ids[0]; vid[1] = ids[1]; vid[2] = ids[2];
+            } else if (plan[0].inner) {
                 // overnight returns of days 2..last of the window: a run of dA[5]-1 gathered rows behind the matrix
                 dA[0] = (int)(h->R + dA[4] + 1);
                 dA[1] = dA[5] - 1;
@@ -651,16 +732,27 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
         h->work_full_rows += (need_hf ? b->hf_hi[w] - b->hf_lo[w] - 1 : 0) + (n - 1);
     }
     for (int ph = 0; ph < 2; ++ph)
-        for (int l = 0; l < 2; ++l) h->work_pre_rows += (double)plan[ph].nb[l] * ((plan[ph].blk[l] + 7) / 8 * 8);
+        for (int l = 0; l < 2; ++l) {
+            if (ph == 0 && l == 0 && plan[0].inner) {
+                for (int k = 0; k < nb0; ++k) h->work_pre_rows += (plan[0].starts[k + 1] - plan[0].starts[k] - 1 + 7) / 8 * 8;
+                continue;
+            }
+            h->work_pre_rows += (double)plan[ph].nb[l] * ((plan[ph].blk[l] + 7) / 8 * 8);
+        }
+    if (presum) h->work_scan_tiles += (double)nb0;
     // descriptors of the block precompute launches: one pseudo-window per block, rows of that block only
     int* bd = gd + (size_t)W * GRAM_DESC_INTS;
     for (int ph = 0; ph < 2; ++ph)
         for (int l = 0; l < 2; ++l) {
             for (int k = 0; k < plan[ph].nb[l]; ++k) {
                 int* d = bd + (size_t)k * GRAM_DESC_INTS + GRAM_PHASE_INTS * ph;
-                d[0] = plan[ph].off + (plan[ph].bmin[l] + k) * plan[ph].blk[l];
-                d[1] = plan[ph].blk[l];
-                if (plan[ph].inner) { d[0] += 1; d[1] -= 1; }
+                if (plan[ph].inner) {           // the day without its overnight return
+                    d[0] = plan[ph].starts[k] + 1;
+                    d[1] = plan[ph].starts[k + 1] - plan[ph].starts[k] - 1;
+                } else {
+                    d[0] = plan[ph].off + (plan[ph].bmin[l] + k) * plan[ph].blk[l];
+                    d[1] = plan[ph].blk[l];
+                }
             }
             out->bdesc[ph][l] = plan[ph].nb[l] ? h->desc + (bd - host) : nullptr;
             out->nblocks[ph][l] = plan[ph].nb[l];
@@ -686,6 +778,18 @@ int upload_batch(bp_handle* h, const bp_window_batch* b, bool need_hf, Batch* ou
     out->fdesc = nfull ? h->desc + (bd - host) : nullptr;
     out->nfull = nfull;
     bd += 3 * (size_t)nfull;
+    if (plan[0].inner) {
+        for (int k = 0; k <= nb0; ++k) bd[k] = plan[0].starts[k];
+        out->hf_starts_dev = h->desc + (bd - host);
+        out->hf_starts = plan[0].starts;
+        bd += (size_t)nb0 + 1;
+        if (presum) {
+            out->hf_vids = h->desc + (bd - host);       // filled per window above
+            bd += 3 * (size_t)W;
+        }
+    }
+    out->presum = presum;
+    out->presum_chunk = plan[0].chunk;
     out->gdesc = h->desc + (size_t)7 * W;
     {
         // banded-GEMM daily pass: worth it when 32 consecutive windows share almost all of their rows
@@ -810,6 +914,9 @@ PrepParams prep_params(const bp_handle* h, const bp_window_batch* b, const Batch
     p.scal = c.scal;
     p.y_ws = c.y;
     p.y_stride = L.y_stride;
+    p.hf_presum = (mode == BP_MODE_CONJUGATE && B.presum) ? 1 : 0;
+    p.hf_vsum = h->vstore;
+    p.hf_vids = B.hf_vids ? B.hf_vids + 3 * (size_t)w0 : nullptr;
     p.use_band = B.band_ok ? 1 : 0;
     p.band_ld = round_up(B.n - 1, 2);
     p.band_aw = B.band_ok ? h->band_aw + (size_t)w0 * p.band_ld : nullptr;
@@ -836,6 +943,13 @@ GramParams gram_params(const bp_handle* h, const Batch& B, const Layout& L, cons
     }
     const bool hf = kind == GRAM_S0 || kind == GRAM_S1;
     const bool daily = kind != GRAM_S0;
+    if (B.presum) {
+        g.store[0][1] = h->store[0][0];          // explicit tile ids into the unified [inner | suffix' | prefix] store
+        if (hf) {
+            g.mv_part = c.mv;
+            g.mv_w0 = c.w0;
+        }
+    }
     g.use_phaseA = hf;
     g.use_phaseB = daily;
     if (hf) {
@@ -926,7 +1040,7 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
     int rc = upload_batch(h, b, mode == BP_MODE_CONJUGATE, &B);
     if (h) h->work_stride = 1;
     if (rc) return rc;
-    const Layout L = make_layout(h, B.max_m);
+    const Layout L = make_layout(h, B.presum ? 0 : B.max_m, B.presum);
     int Wc = (int)std::min<size_t>((size_t)B.W, std::max<size_t>(1, h->ws_limit / L.per_window));
     // (the descriptors were planned for the base windows only: the chain path must not be abandoned after upload_batch;
     // the check above uses the same layout, so this cannot trigger unless the two are changed apart)
@@ -934,7 +1048,7 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
     // Pipelined against a segmented asynchronous intraday upload: prep + Gram of the windows whose bars have
     // arrived run while the rest is still being copied; the solve follows for all windows at once.
     const bool pipelined = mode == BP_MODE_CONJUGATE && h->hf_pending && h->n_seg > 1 && h->seg_waited < h->n_seg &&
-                           solve && !out->T && !out->S0 && Wc >= B.W;
+                           solve && !out->T && !out->S0 && Wc >= B.W && !B.presum;
     if (mode == BP_MODE_CONJUGATE && !pipelined && (rc = wait_hf(h))) return rc;
     rc = ensure_ws(h, (size_t)Wc * L.per_window + 256);
     if (rc) return rc;
@@ -961,13 +1075,22 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
 
     const bool any_gram = out->T || out->S0 || out->S1 || solve;
     if (any_gram && !pipelined) {
-        if (mode == BP_MODE_CONJUGATE && B.hf_inner) {
-            launch_gather_strided_rows(h->lr_hf, h->ld, (long long)B.hf_off + (long long)B.hf_bmin[0] * B.hf_blk[0], B.hf_blk[0],
-                                       h->R, 0, B.hf_nb0, h->stream);
+        if (mode == BP_MODE_CONJUGATE && B.hf_inner && !B.presum) {
+            launch_gather_rows_indexed(h->lr_hf, h->ld, B.hf_starts_dev, h->R, 0, B.hf_nb0, h->stream);
             h->launches++;
             CU_TRY(cudaGetLastError());
         }
-        if (mode == BP_MODE_CONJUGATE && (out->S0 || out->S1 || solve) && (rc = run_block_precompute(h, B, 0))) return rc;
+        if (mode == BP_MODE_CONJUGATE && (out->S0 || out->S1 || solve || B.presum) && (rc = run_block_precompute(h, B, 0))) return rc;
+        if (mode == BP_MODE_CONJUGATE && B.presum) {
+            // scans of the day blocks: column sums (vectors) and Gram tiles, suffix' and prefix per chunk
+            StageTimer tm(h, BP_STAGE_GRAM);
+            const int nt = (N + GRAM_TILE - 1) / GRAM_TILE;
+            launch_block_col_sums(h->lr_hf, h->ld, B.hf_starts_dev, 0, B.hf_nb0, h->vstore, h->stream);
+            launch_vec_scan(h->vstore, h->ld, h->lr_hf, B.hf_starts_dev, B.hf_nb0, B.presum_chunk, h->stream);
+            launch_tile_scan(h->store[0][0], nt * (nt + 1) / 2, nt, h->lr_hf, h->ld, B.hf_starts_dev, B.hf_nb0, B.presum_chunk, h->stream);
+            h->launches += 3;
+            CU_TRY(cudaGetLastError());
+        }
         if ((out->T || out->S1 || solve) && (rc = run_block_precompute(h, B, 1))) return rc;
     }
     // Cholesky + solves of the windows [ws, ws+wn) of the workspace
@@ -1018,14 +1141,18 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
             int k_ready[2];
             for (int l = 0; l < 2; ++l) {
                 k_ready[l] = B.nblocks[0][l];
-                if (!last && B.hf_blk[l] > 0) {
+                if (!last && l == 0 && B.hf_inner) {
+                    // day block k is complete once the bars below starts[k+1] have arrived
+                    const long long k = std::upper_bound(B.hf_starts.begin() + 1, B.hf_starts.end(), (int)std::min<long long>(r_end, 0x7fffffff)) -
+                                        (B.hf_starts.begin() + 1);
+                    k_ready[l] = (int)std::min<long long>(B.nblocks[0][l], std::max<long long>(k, k_done[l]));
+                } else if (!last && B.hf_blk[l] > 0) {
                     const long long k = floor_div(r_end - B.hf_off, B.hf_blk[l]) - B.hf_bmin[l];
                     k_ready[l] = (int)std::min<long long>(B.nblocks[0][l], std::max<long long>(k, k_done[l]));
                 }
             }
             if (B.hf_inner) {
-                launch_gather_strided_rows(h->lr_hf, h->ld, (long long)B.hf_off + (long long)B.hf_bmin[0] * B.hf_blk[0],
-                                           B.hf_blk[0], h->R, k_done[0], k_ready[0], h->stream);
+                launch_gather_rows_indexed(h->lr_hf, h->ld, B.hf_starts_dev, h->R, k_done[0], k_ready[0], h->stream);
                 h->launches++;
                 CU_TRY(cudaGetLastError());
             }
@@ -1084,10 +1211,33 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
             rc = emit_sym(h, c.S, L, wc, out->T + om);
             if (rc) return rc;
         }
-        if (out->S0 && mode == BP_MODE_CONJUGATE) {
+        // pre-summed day blocks: S0 w0, v0, c and rhs are finished from the G w0 partials of the first Gram launch
+        // that contracts the intraday phase (it must precede the solve and every emit of rhs / scalars)
+        bool post_pending = mode == BP_MODE_CONJUGATE && B.presum;
+        auto run_post = [&]() -> int {
+            if (!post_pending) return BP_OK;
+            post_pending = false;
+            PostParams q{};
+            q.n_windows = wc;
+            q.n_assets = N;
+            q.ldv = L.ldv;
+            q.mv_part = c.mv;
+            q.w0 = c.w0;
+            q.gvec = c.gvec;
+            q.t = c.t;
+            q.s0w0 = c.s0w0;
+            q.rhs = c.rhs;
+            q.scal = c.scal;
+            StageTimer tm(h, BP_STAGE_PREP);
+            CU_TRY(launch_conj_post(q, h->stream));
+            h->launches++;
+            return BP_OK;
+        };
+        if ((out->S0 || (post_pending && !solve && !out->S1)) && mode == BP_MODE_CONJUGATE) {
             rc = run_gram(h, gram_params(h, B, L, c, w0, wc, GRAM_S0), B.resampled);
             if (rc) return rc;
-            rc = emit_sym(h, c.S, L, wc, out->S0 + om);
+            if ((rc = run_post())) return rc;
+            rc = emit_sym(h, c.S, L, wc, out->S0 ? out->S0 + om : nullptr);
             if (rc) return rc;
         }
         if (solve || out->S1) {
@@ -1099,6 +1249,7 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
                 }
                 rc = run_gram(h, gp, B.resampled);
                 if (rc) return rc;
+                if ((rc = run_post())) return rc;
             }
             if (estimator == BP_EST_SHRINKAGE) {
                 // C = X_c'X_c  ->  m Sigma_LW / (1 - shrinkage) = C + rho I, rhs = t / (1 - shrinkage), in place (:727-729)
@@ -1243,6 +1394,7 @@ int bp_destroy(bp_handle* h) {
     cudaFree(h->rstore[0]);
     cudaFree(h->rstore[1]);
     cudaFree(h->fstore);
+    cudaFree(h->vstore);
     cudaFree(h->prior_n);
     cudaFree(h->band_aw);
     cudaFree(h->band_stats);
@@ -1326,6 +1478,13 @@ int bp_get_solve_work(bp_handle* h, double* out2) {
     out2[0] = h->work_factored;
     out2[1] = h->work_chained;
     h->work_factored = h->work_chained = 0;
+    return BP_OK;
+}
+
+int bp_set_hf_presum_min_days(bp_handle* h, int min_days) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    if (min_days < 0) return fail(BP_ERR_INVALID, "min_days must be >= 0");
+    h->presum_min_days = min_days;
     return BP_OK;
 }
 

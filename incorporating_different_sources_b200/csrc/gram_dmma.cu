@@ -154,12 +154,15 @@ __device__ __forceinline__ void add_half(const unsigned char* s, double (&acc)[8
     }
 }
 
+// MV: also emit the G w0 by-product of phase A (a second instantiation, so that the plain kernel keeps its registers)
+template <bool MV>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_dmma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                  const GramParams p) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t full_bar[GRAM_STAGES];
     __shared__ uint64_t empty_bar[GRAM_STAGES];    // one arrival per consumer warp: no block barrier per item
+    __shared__ double mv_red[MV ? 6 : 1][GRAM_TILE];   // cross-warp partials of the optional G w0 by-product
     // 1024-byte alignment for the 128B swizzle, by pointer arithmetic on the shared array itself so that
     // the compiler keeps the shared address space (an integer round trip degrades every LDS to a generic LD)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -266,6 +269,56 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);      // this warp is done with the stage
             if (tid == 0 && pvalid) producer_issue();
+            if (MV && f == js.end[4] - 1) {
+                // by-product of phase A: the raw intraday Gram tile times the prior weights (S0 w0 without a pass over
+                // the window's own rows).  Row direction: y_i += sum_j G_ij w0_j; column direction (off-diagonal
+                // tiles stand for their mirror image too): y_j += sum_i G_ij w0_i.  Partials per tile, fixed order.
+                const double* w0 = p.mv_w0 + (long long)js.w * p.ldv;
+                const int jb = js.tj * GRAM_TILE + warp_n0 + 2 * tig;
+                const int ib = js.ti * GRAM_TILE + warp_m0 + g;
+                double wj[4][2];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = jb + nt * 8 + e;
+                        wj[nt][e] = j < p.ldv ? w0[j] : 0.0;
+                    }
+                __syncthreads();                           // the previous job's readers of mv_red are done
+#pragma unroll
+                for (int mt = 0; mt < 8; ++mt) {
+                    double r = 0.0;
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) r = fma(acc[mt][nt][0], wj[nt][0], fma(acc[mt][nt][1], wj[nt][1], r));
+                    r += __shfl_xor_sync(0xffffffffu, r, 1);
+                    r += __shfl_xor_sync(0xffffffffu, r, 2);
+                    if (tig == 0) mv_red[warp >> 1][warp_m0 + mt * 8 + g] = r;
+                }
+                if (!diag) {
+                    double wi[8];
+#pragma unroll
+                    for (int mt = 0; mt < 8; ++mt) {
+                        const int i = ib + mt * 8;
+                        wi[mt] = i < p.ldv ? w0[i] : 0.0;
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            double c = 0.0;
+#pragma unroll
+                            for (int mt = 0; mt < 8; ++mt) c = fma(acc[mt][nt][e], wi[mt], c);
+                            c += __shfl_xor_sync(0xffffffffu, c, 4);
+                            c += __shfl_xor_sync(0xffffffffu, c, 8);
+                            c += __shfl_xor_sync(0xffffffffu, c, 16);
+                            if (g == 0) mv_red[4 + (warp & 1)][warp_n0 + nt * 8 + 2 * tig + e] = c;
+                        }
+                }
+                __syncthreads();
+                double* dst = p.mv_part + ((long long)js.w * npairs + js.pair) * (2 * GRAM_TILE);
+                if (tid < GRAM_TILE) dst[tid] = (mv_red[0][tid] + mv_red[1][tid]) + (mv_red[2][tid] + mv_red[3][tid]);
+                else dst[tid] = diag ? 0.0 : mv_red[4][tid - GRAM_TILE] + mv_red[5][tid - GRAM_TILE];
+            }
             if (f == js.end[4] - 1 && p.use_alpha) {      // last item of phase A: scale the HF Gram
                 const double alpha = p.scal[(long long)js.w * BP_S_COUNT + BP_S_ALPHA];
 #pragma unroll
@@ -339,14 +392,19 @@ cudaError_t launch_gram(const GramParams& p, const CUtensorMap& map0, const CUte
     if (p.n_windows <= 0) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gram_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(gram_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const int nt = (p.n_assets + GRAM_TILE - 1) / GRAM_TILE;
     const long long njobs = (long long)p.n_windows * (nt * (nt + 1) / 2);
     const int grid = (int)(njobs < sm_count ? njobs : sm_count);
-    gram_dmma_kernel<<<grid, GRAM_THREADS, GRAM_SMEM, st>>>(map0, map1, p);
+    if (p.mv_part && p.use_phaseA && !p.tile_store_out)
+        gram_dmma_kernel<true><<<grid, GRAM_THREADS, GRAM_SMEM, st>>>(map0, map1, p);
+    else
+        gram_dmma_kernel<false><<<grid, GRAM_THREADS, GRAM_SMEM, st>>>(map0, map1, p);
     return cudaGetLastError();
 }
 

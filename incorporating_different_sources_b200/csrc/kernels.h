@@ -70,6 +70,12 @@ struct PrepParams {
     double* y_ws;             // [W][y_stride] scratch for the HF row dots
     long long y_stride;
     // banded-GEMM form of the daily pass (band_prep.cu), used for batches of consecutive trade dates
+    // Pre-summed intraday day blocks (long HF look-backs, bp_api.cu "presum"): the window's column sums come from the
+    // scanned per-day column sums instead of a pass over its own rows, and S0 w0 / v0 / c / rhs are finished by
+    // conj_post_kernel from the mat-vec partials the Gram kernel leaves behind
+    int hf_presum;
+    const double* hf_vsum;    // [3 nb][ld]: suffix' sums at nb + b, prefix sums at 2 nb + b (same ids as the tile store)
+    const int* hf_vids;       // [W][3] ids into hf_vsum (-1 = absent)
     int beta_den;             // Jeffreys-mode rank-1 coefficient beta = 1 / beta_den (0: n_window, :600; estimators: n-1)
     int use_band;
     double* band_aw;          // [W][band_ld] risk-free weights a_k(w)
@@ -109,7 +115,36 @@ struct GramParams {
     const double* pvec;      // [W][ldv] or nullptr
     const double* gvec;      // [W][ldv] or nullptr
     double* out;             // [W][win_stride]  (or the tile store in tile_store_out mode)
+    // optional by-product of phase A: the raw intraday Gram times the prior weights, G w0, as per-tile partial sums
+    // mv_part[((w * npairs + pair) * 2 + dir) * 128 + k]: dir 0 = rows of tile row ti (sum over the tile's columns),
+    // dir 1 = columns of tile column tj (sum over the tile's rows; off-diagonal tiles only).  Reduced in a fixed
+    // order by conj_post_kernel: no atomics, bit-reproducible.
+    double* mv_part;
+    const double* mv_w0;     // [W][ldv] prior weights
 };
+
+// S0 w0 = alpha (G w0 - m hbar (hbar'w0)), v0 = w0'S0w0 (:64-88), c (:415-418), rhs = c S0w0 + t (:489) from the
+// mat-vec partials of the Gram kernel (pre-summed day blocks: no pass over the window's own intraday rows)
+struct PostParams {
+    int n_windows, n_assets, ldv;
+    const double* mv_part;   // [W][npairs][2][128]
+    const double* w0;        // [W][ldv]
+    const double* gvec;      // [W][ldv] hbar
+    const double* t;         // [W][ldv]
+    double* s0w0;            // [W][ldv]
+    double* rhs;             // [W][ldv]
+    double* scal;            // [W][BP_S_COUNT] reads n0, alpha, m; writes c, v0
+};
+cudaError_t launch_conj_post(const PostParams& p, cudaStream_t st);
+// column sums of the inner rows (all but the first) of every block: out[b][ld], blocks given by starts[b], starts[b+1]
+void launch_block_col_sums(const double* M, int ld, const int* starts, int b0, int b1, double* out, cudaStream_t st);
+// Scans over chunks of `chunk` consecutive blocks (suffix' at nb + b, prefix at 2 nb + b, see bp_api.cu):
+//   FD[b] = inner[b] + overnight[b] (vectors) or inner tile + overnight (x) overnight (tiles)
+//   prefix[b]  = FD[chunk start] + ... + FD[b]          suffix'[b] = inner[b] + FD[b+1] + ... + FD[chunk end]
+void launch_vec_scan(double* vsum, int ld, const double* M, const int* starts, int nb, int chunk, cudaStream_t st);
+void launch_tile_scan(double* store, int npairs, int n_tiles_side, const double* M, int ld, const int* starts, int nb,
+                      int chunk, cudaStream_t st);
+void launch_gather_rows_indexed(double* M, int ld, const int* src_rows, long long dst_row0, int k0, int k1, cudaStream_t st);
 
 struct SolveParams {
     int n_windows;

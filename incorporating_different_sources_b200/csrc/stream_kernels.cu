@@ -277,9 +277,41 @@ __global__ void __launch_bounds__(PREP_THREADS, 2) window_prep_kernel(PrepParams
     }
     __syncthreads();
 
+    const int m = p.hf_m[w];                                // HF returns in the window
+    if (p.hf_presum) {
+        // pre-summed day blocks: the window's column sums are <= 3 scanned vectors (suffix' + whole chunk + prefix);
+        // S0 w0, v0, c and rhs follow the Gram launch (conj_post_kernel)
+        const int* ids = p.hf_vids + 3 * (long long)w;
+        for (int c = tid * 2; c < p.ldv; c += 2 * PREP_THREADS) {
+            double2 hs = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (ids[k] >= 0) {
+                    const double2 v = *reinterpret_cast<const double2*>(p.hf_vsum + (long long)ids[k] * p.ld + c);
+                    hs.x += v.x;
+                    hs.y += v.y;
+                }
+            }
+            double2 hb = make_double2(c < N ? hs.x / (double)m : 0.0, c + 1 < N ? hs.y / (double)m : 0.0);
+            *reinterpret_cast<double2*>(p.gvec + (long long)w * p.ldv + c) = hb;
+        }
+        if (tid == 0) {
+            const double alpha = n0 * ((double)m / (double)(m - 1));   // S0 = n0 * cov * m  (:317-318, :333)
+            scal[BP_S_N0] = n0;
+            scal[BP_S_N1] = n1;
+            scal[BP_S_ALPHA] = alpha;
+            scal[BP_S_BETA] = alpha * (double)m;
+            scal[BP_S_C] = 0.0;
+            scal[BP_S_V0] = 0.0;
+            scal[BP_S_M] = (double)m;
+            scal[BP_S_SUMA] = sa;
+            scal[BP_S_MCM_AVG] = avg;
+        }
+        return;
+    }
+
     // ---- HF pass 1: column means hbar and row dots y_k = h_k . w0   (:314-318)
     const long long h0 = (long long)p.hf_row0[w];           // first HF return row (first bar dropped, F5)
-    const int m = p.hf_m[w];                                // HF returns in the window
     double* y = p.y_ws + (long long)w * p.y_stride;
     const bool one_pass = p.ldv <= 512;
     double2 hs1 = make_double2(0.0, 0.0), q1 = make_double2(0.0, 0.0);
@@ -489,6 +521,185 @@ void launch_gather_strided_rows(double* M, int ld, long long src_row0, int strid
                                 cudaStream_t st) {
     if (k1 <= k0) return;
     gather_strided_rows_kernel<<<k1 - k0, 128, 0, st>>>(M, ld, src_row0, stride, dst_row0, k0, k1);
+}
+
+// dst row (dst_row0 + k) = src row src_rows[k], k in [k0, k1): the overnight returns of arbitrary day blocks
+__global__ void gather_rows_indexed_kernel(double* __restrict__ M, int ld, const int* __restrict__ src_rows,
+                                           long long dst_row0, int k0, int k1) {
+    const int k = k0 + blockIdx.x;
+    if (k >= k1) return;
+    const double2* src = reinterpret_cast<const double2*>(M + (long long)src_rows[k] * ld);
+    double2* dst = reinterpret_cast<double2*>(M + (dst_row0 + k) * ld);
+    for (int c = threadIdx.x; c < ld / 2; c += blockDim.x) dst[c] = src[c];
+}
+
+void launch_gather_rows_indexed(double* M, int ld, const int* src_rows, long long dst_row0, int k0, int k1,
+                                cudaStream_t st) {
+    if (k1 <= k0) return;
+    gather_rows_indexed_kernel<<<k1 - k0, 128, 0, st>>>(M, ld, src_rows, dst_row0, k0, k1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pre-summed intraday day blocks (long HF look-backs).  A window of D trading days is
+//   inner(first day) + FD(day 2) + ... + FD(day D),   FD(b) = inner(b) + overnight(b) (x) overnight(b)
+// (inner = the day without its first, overnight, return; the window's own first bar has no return, F5).  With the
+// days cut into chunks of C consecutive blocks (C = the shortest run of full days of any window) and, per chunk,
+//   prefix[b]  = FD[chunk start] + ... + FD[b]               suffix'[b] = inner[b] + FD[b+1] + ... + FD[chunk end]
+// every window is suffix'[first day] + (one whole chunk = prefix[chunk end])? + prefix[last day]: at most three
+// stored tiles / vectors whatever the look-back, all exact FP64 sums of the same products (no subtraction).
+// The same ids address the tile store (bp_api.cu) and the vector store: inner at b, suffix' at nb + b, prefix at 2nb + b.
+
+// column sums of the inner rows of blocks [b0, b1): out[b][ld]
+__global__ void block_col_sums_kernel(const double* __restrict__ M, int ld, const int* __restrict__ starts, int b0,
+                                      double* __restrict__ out) {
+    const int b = b0 + blockIdx.x;
+    const int r0 = starts[b] + 1, r1 = starts[b + 1];
+    for (int c = threadIdx.x * 2; c < ld; c += 2 * blockDim.x) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int r = r0; r < r1; ++r) {
+            const double2 v = *reinterpret_cast<const double2*>(M + (long long)r * ld + c);
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+        *reinterpret_cast<double2*>(out + (long long)b * ld + c) = acc;
+    }
+}
+
+void launch_block_col_sums(const double* M, int ld, const int* starts, int b0, int b1, double* out, cudaStream_t st) {
+    if (b1 <= b0) return;
+    block_col_sums_kernel<<<b1 - b0, 128, 0, st>>>(M, ld, starts, b0, out);
+}
+
+// vsum rows [0, nb) hold the inner column sums; writes suffix' rows at nb + b and prefix rows at 2 nb + b
+__global__ void vec_scan_kernel(double* __restrict__ vsum, int ld, const double* __restrict__ M,
+                                const int* __restrict__ starts, int nb, int chunk) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (c >= ld) return;
+    const int lo = blockIdx.y * chunk, hi = min(lo + chunk, nb);
+    double2 acc = make_double2(0.0, 0.0);
+    for (int b = lo; b < hi; ++b) {
+        const double2 in = *reinterpret_cast<const double2*>(vsum + (long long)b * ld + c);
+        const double2 o = b > 0 ? *reinterpret_cast<const double2*>(M + (long long)starts[b] * ld + c) : make_double2(0.0, 0.0);
+        acc.x += in.x + o.x;
+        acc.y += in.y + o.y;
+        *reinterpret_cast<double2*>(vsum + (long long)(2 * nb + b) * ld + c) = acc;
+    }
+    acc = make_double2(0.0, 0.0);
+    for (int b = hi - 1; b >= lo; --b) {
+        const double2 in = *reinterpret_cast<const double2*>(vsum + (long long)b * ld + c);
+        const double2 o = b > 0 ? *reinterpret_cast<const double2*>(M + (long long)starts[b] * ld + c) : make_double2(0.0, 0.0);
+        *reinterpret_cast<double2*>(vsum + (long long)(nb + b) * ld + c) = make_double2(in.x + acc.x, in.y + acc.y);
+        acc.x += in.x + o.x;
+        acc.y += in.y + o.y;
+    }
+}
+
+void launch_vec_scan(double* vsum, int ld, const double* M, const int* starts, int nb, int chunk, cudaStream_t st) {
+    if (nb <= 0) return;
+    dim3 grid((ld / 2 + 127) / 128, (nb + chunk - 1) / chunk);
+    vec_scan_kernel<<<grid, 128, 0, st>>>(vsum, ld, M, starts, nb, chunk);
+}
+
+// Tile version: store tiles [0, nb) x npairs hold the inner Gram tiles (fragment-major, as written by the block
+// precompute of gram_dmma_kernel); one thread per double2 of a tile, sequential over the blocks of its chunk.
+// Element (q, t) of a tile, q = 4 mt + nt, t = thread of the Gram CTA: row 128 ti + 64 (warp & 1) + 8 mt + g,
+// columns 128 tj + 32 (warp >> 1) + 8 nt + 2 tig (+1).
+__global__ void __launch_bounds__(256) tile_scan_kernel(double* __restrict__ store, int npairs, const double* __restrict__ M,
+                                                        int ld, const int* __restrict__ starts, int nb, int chunk) {
+    const int idx2 = blockIdx.x * blockDim.x + threadIdx.x;      // double2 index inside the tile, < 8192
+    const int pair = blockIdx.y;
+    const int lo = blockIdx.z * chunk, hi = min(lo + chunk, nb);
+    int ti = 0;
+    while ((ti + 1) * (ti + 2) / 2 <= pair) ++ti;
+    const int tj = pair - ti * (ti + 1) / 2;
+    const int q = idx2 >> 8, t = idx2 & 255;
+    const int warp = t >> 5, lane = t & 31, g = lane >> 2, tig = lane & 3;
+    const int i = ti * GRAM_TILE + (warp & 1) * 64 + (q >> 2) * 8 + g;
+    const int j = tj * GRAM_TILE + (warp >> 1) * 32 + (q & 3) * 8 + 2 * tig;
+    const bool in_i = i < ld, in_j = j < ld;                      // ld is even: j + 1 < ld whenever j < ld
+    const long long tile2 = GRAM_BLOCK_TILE_DOUBLES / 2;
+    double2* S = reinterpret_cast<double2*>(store);
+    auto at = [&](long long id) { return S + (id * npairs + pair) * tile2 + idx2; };
+    auto rank1 = [&](int b) {
+        double2 r = make_double2(0.0, 0.0);
+        if (b > 0 && in_i && in_j) {
+            const double* o = M + (long long)starts[b] * ld;
+            const double oi = o[i];
+            const double2 oj = *reinterpret_cast<const double2*>(o + j);
+            r.x = oi * oj.x;
+            r.y = oi * oj.y;
+        }
+        return r;
+    };
+    double2 acc = make_double2(0.0, 0.0);
+    for (int b = lo; b < hi; ++b) {
+        const double2 in = *at(b);
+        const double2 r = rank1(b);
+        acc.x += in.x + r.x;
+        acc.y += in.y + r.y;
+        *at(2LL * nb + b) = acc;
+    }
+    acc = make_double2(0.0, 0.0);
+    for (int b = hi - 1; b >= lo; --b) {
+        const double2 in = *at(b);
+        const double2 r = rank1(b);
+        *at((long long)nb + b) = make_double2(in.x + acc.x, in.y + acc.y);
+        acc.x += in.x + r.x;
+        acc.y += in.y + r.y;
+    }
+}
+
+void launch_tile_scan(double* store, int npairs, int n_tiles_side, const double* M, int ld, const int* starts, int nb,
+                      int chunk, cudaStream_t st) {
+    (void)n_tiles_side;
+    if (nb <= 0) return;
+    dim3 grid(GRAM_BLOCK_TILE_DOUBLES / 2 / 256, npairs, (nb + chunk - 1) / chunk);
+    tile_scan_kernel<<<grid, 256, 0, st>>>(store, npairs, M, ld, starts, nb, chunk);
+}
+
+// S0 w0, v0, c, rhs from the Gram kernel's mat-vec partials (see PostParams)
+__global__ void __launch_bounds__(256) conj_post_kernel(PostParams p) {
+    __shared__ double scratch[40];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const int N = p.n_assets;
+    const int nt = (N + GRAM_TILE - 1) / GRAM_TILE;
+    const int npairs = nt * (nt + 1) / 2;
+    const double* part = p.mv_part + (long long)w * npairs * 256;
+    const double* w0 = p.w0 + (long long)w * p.ldv;
+    const double* hb = p.gvec + (long long)w * p.ldv;
+    double* scal = p.scal + (long long)w * BP_S_COUNT;
+    const double n0 = scal[BP_S_N0], alpha = scal[BP_S_ALPHA], m = scal[BP_S_M];
+    double hw = 0.0;
+    for (int i = tid; i < N; i += 256) hw = fma(hb[i], w0[i], hw);
+    hw = block_sum(hw, scratch);                                   // hbar'w0
+    double v0p = 0.0;
+    for (int i = tid; i < p.ldv; i += 256) {
+        double s0 = 0.0;
+        if (i < N) {
+            const int ti = i / GRAM_TILE, k = i % GRAM_TILE;
+            double raw = 0.0;
+            for (int tj = 0; tj <= ti; ++tj) raw += part[((ti * (ti + 1) / 2 + tj) * 2 + 0) * 128 + k];        // tiles of row ti
+            for (int tk = ti + 1; tk < nt; ++tk) raw += part[((tk * (tk + 1) / 2 + ti) * 2 + 1) * 128 + k];    // tiles of column ti
+            s0 = alpha * fma(-m * hw, hb[i], raw);                // S0 w0 = alpha (G w0 - m hbar (hbar'w0))
+            v0p = fma(w0[i], s0, v0p);
+        }
+        p.s0w0[(long long)w * p.ldv + i] = s0;
+    }
+    const double v0 = block_sum(v0p, scratch);
+    const double kk = n0 + (double)N + 2.0;
+    const double cc = (2.0 * n0) / (kk + sqrt(kk * kk + 4.0 * n0 * v0));   // :415-418
+    for (int i = tid; i < p.ldv; i += 256)
+        p.rhs[(long long)w * p.ldv + i] = i < N ? fma(cc, p.s0w0[(long long)w * p.ldv + i], p.t[(long long)w * p.ldv + i]) : 0.0;
+    if (tid == 0) {
+        scal[BP_S_C] = cc;
+        scal[BP_S_V0] = v0;
+    }
+}
+
+cudaError_t launch_conj_post(const PostParams& p, cudaStream_t st) {
+    if (p.n_windows <= 0) return cudaSuccess;
+    conj_post_kernel<<<p.n_windows, 256, 0, st>>>(p);
+    return cudaGetLastError();
 }
 
 // One tile per distinct RUN TRIPLE (coarse run + fine run on the head side + fine run on the tail side): the three

@@ -146,6 +146,13 @@ class BayesEngine:
         if rc:
             _raise(rc)
 
+    def set_hf_presum_min_days(self, min_days: int = 8):
+        """Windows whose intraday look-back covers at least ``min_days`` trading days add at most three pre-summed
+        (scanned) day-block tiles instead of one tile per day; 0 disables."""
+        rc = self._lib.bp_set_hf_presum_min_days(self._h, int(min_days))
+        if rc:
+            _raise(rc)
+
     def set_async_outputs(self, enable: bool):
         """Batched calls with page-locked HOST outputs (``into=``) return once queued; results are complete after
         ``synchronize()``.  The host can then plan the next batch while the GPU works on the previous one."""
@@ -407,11 +414,12 @@ class BayesEngine:
 
     # ------------------------------------------------------------------ loop body
     def backtest_loop(self, reb_rows, weights, distance_scale: float, turnover_cost_bps: float, member=None,
-                      last_row: Optional[int] = None):
+                      last_row: Optional[int] = None, device_out: bool = False):
         """Loop body of ``Portfolio.update_portfolio`` (:1127-1219) for a whole backtest.
 
         ``reb_rows`` [R] daily rows of the rebalance dates, ``weights`` [R][N] (NumPy, or a CUDA torch tensor
-        as returned by ``conjugate(..., device_out=True)``).  Returns (returns [T], turnover [R-1], metrics [R][5]).
+        as returned by ``conjugate(..., device_out=True)``).  Returns (returns [T], turnover [R-1], metrics [R][5]),
+        NumPy arrays or, with ``device_out``, CUDA tensors (no device -> host copy).
         """
         reb = np.ascontiguousarray(reb_rows, dtype=np.int32)
         R = int(reb.shape[0])
@@ -443,10 +451,18 @@ class BayesEngine:
         d.distance_scale = float(distance_scale)
         d.turnover_cost_bps = float(turnover_cost_bps)
         T = int(last_row - reb[0]) if R else 0
-        rets = np.empty(max(T, 0))
-        to = np.empty(max(R - 1, 0))
-        met = np.empty((R, 5))
-        d.returns, d.turnover, d.metrics = rets.ctypes.data, to.ctypes.data, met.ctypes.data
+        if device_out:
+            torch = self._torch
+            dev = f"cuda:{self.device}"
+            rets = torch.empty(max(T, 1), dtype=torch.float64, device=dev)[:max(T, 0)]
+            to = torch.empty(max(R - 1, 1), dtype=torch.float64, device=dev)[:max(R - 1, 0)]
+            met = torch.empty((R, 5), dtype=torch.float64, device=dev)
+            d.returns, d.turnover, d.metrics = rets.data_ptr(), to.data_ptr(), met.data_ptr()
+        else:
+            rets = np.empty(max(T, 0))
+            to = np.empty(max(R - 1, 0))
+            met = np.empty((R, 5))
+            d.returns, d.turnover, d.metrics = rets.ctypes.data, to.ctypes.data, met.ctypes.data
         rc = self._lib.bp_backtest_batched(self._h, C.byref(d))
         del keep
         if rc:

@@ -113,3 +113,80 @@ def engine_compute(engine, mkt, spec, hf_lookback_days=None, outputs=("weights",
         res = fn(batch, outputs=tuple(outputs), device_out=True)
         return res[outputs[0]]
     return compute
+
+
+class ShardedBacktest:
+    """One rank's share of ONE backtest split by contiguous date range (the north-star partition): conjugate and
+    Jeffreys weights of its rebalance dates plus the loop body (daily returns, turnover, :1127-1219) of its range.
+
+    Resident rows = the rank's own trading days, the ``rolling_window - 1`` daily rows before them (halo of the longer
+    of the two windows) and the intraday bars of its dates' look-backs.  The loop body at the first own date needs
+    the weights chosen at the previous rebalance date (:1134-1159, :1212), so every rank but the first also
+    evaluates that ONE predecessor window (the one-window halo of SURVEY 8(e)) instead of receiving it.
+    ``gather()`` all-gathers ``[2][W_local][N]`` weights and the ``[W_local]`` return / turnover rows — the only
+    communication of the path."""
+
+    def __init__(self, engine, mkt, conj_spec, jeff_spec, d_indices, rank: int, world: int,
+                 hf_lookback_days: Optional[int] = None, pin=None):
+        from .windows import ffill_rows, plan_daily_windows, trim_intraday
+        self.engine, self.rank, self.world = engine, rank, world
+        d_all = np.asarray(d_indices, dtype=np.int64)
+        if len(d_all) < world or np.any(np.diff(d_all) != 1):
+            raise ValueError("ShardedBacktest splits a DAILY-rebalance backtest: consecutive trading dates, >= 1 per rank")
+        self.counts = [hi - lo for lo, hi in partition(len(d_all), world)]
+        lo, hi = partition(len(d_all), world)[rank]
+        self.lo, self.hi = lo, hi
+        self.halo = 1 if lo > 0 else 0
+        ext = d_all[lo - self.halo:hi]                       # predecessor window first (ranks > 0)
+        self.n_ext = len(ext)
+        n_max = max(int(conj_spec["rolling_window"]), int(jeff_spec["rolling_window"]))
+        day_lo, day_hi = int(ext.min()) - (n_max - 1), int(ext.max()) + 1
+        if day_lo < 0:
+            raise ValueError("not enough history before the first rebalance date of this shard")
+        dates = mkt.dates[day_lo:day_hi]
+        self.cb = plan_daily_windows(conj_spec, dates, ext - day_lo, mkt.hf_ts, hf_lookback_days=hf_lookback_days)
+        self.jb = plan_daily_windows(jeff_spec, dates, ext - day_lo, need_hf=False)
+        h_lo, h_hi = trim_intraday(self.cb)                  # rows of mkt.hf_prices this rank's windows read
+        rf_dates = getattr(mkt, "rf_dates", mkt.dates)
+        pin = pin or (lambda a: np.ascontiguousarray(a))
+        self.host = dict(prices=pin(mkt.prices[day_lo:day_hi]), caps=pin(mkt.caps[day_lo:day_hi]),
+                         hf_prices=pin(mkt.hf_prices[h_lo:h_hi]),
+                         mcm=pin(np.stack([mkt.vix[day_lo:day_hi], mkt.epu[day_lo:day_hi]])),
+                         rf_row=pin(ffill_rows(dates, rf_dates, mkt.rf)))
+        self.h2d_bytes = int(sum(v.nbytes for v in self.host.values()))
+        self.reb_rows = (ext - day_lo).astype(np.int32)
+        self.gamma_c = float(conj_spec["risk_aversion"])
+        self.gamma_j = float(jeff_spec["risk_aversion"])
+        self.cost = float(conj_spec["turnover_cost"])
+        self.n_assets = mkt.n_assets
+
+    def upload(self, async_copy: bool = False):
+        self.engine.upload_market(**self.host, async_copy=async_copy)
+
+    def compute(self, out_c, out_j, loop: bool = True):
+        """Weights of the shard's windows into ``out_c`` / ``out_j`` (dicts with 'weights' [n_ext][N] and 'status'
+        CUDA tensors) and, with ``loop``, the loop body of both strategies.  Returns the local rows to gather:
+        (weights_c, weights_j, returns_c, returns_j, turnover_c, turnover_j) without the halo window."""
+        eng = self.engine
+        eng.conjugate(self.cb, outputs=("weights", "status"), into=out_c)
+        eng.jeffreys(self.jb, outputs=("weights", "status"), into=out_j)
+        k = self.halo
+        res = [out_c["weights"][k:], out_j["weights"][k:]]
+        if loop:
+            for w, g in ((out_c["weights"], self.gamma_c), (out_j["weights"], self.gamma_j)):
+                r, to, _ = eng.backtest_loop(self.reb_rows, w, distance_scale=g, turnover_cost_bps=self.cost,
+                                             device_out=True)
+                res += [r, to]
+            res = [res[0], res[1], res[2], res[4], res[3], res[5]]
+        return res
+
+    def gather(self, rows, dist, group=None):
+        """All-gather per-date rows of every rank in date order.  Rank 0 has one return / turnover row fewer than
+        rebalance dates (the backtest's first date has no return, :1132): counts are adjusted per tensor."""
+        out = []
+        for x in rows:
+            cnt = list(self.counts)
+            if x.shape[0] == self.hi - self.lo - (1 if self.rank == 0 else 0) and x.dim() == 1:
+                cnt[0] -= 1
+            out.append(gather_rows(x, cnt, dist, group))
+        return out

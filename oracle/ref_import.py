@@ -14,8 +14,9 @@ Two stub modules are registered in ``sys.modules`` before the import; the only
 stub function ever called on the hot path is ``extract_unique_tickers``
 (``portfolio_calculations.py:619``).
 
-This only works where ``/root/reference`` exists (the build container).  Nothing
-under ``-m gpu`` tests, ``smoke()`` or ``bench.py`` may call it.
+Sources are looked up at ``$REF_SRC``, ``/root/reference/src`` (build container) and ``baseline/_ref/src`` (the
+git-ignored staging copy ``__graft_entry__.build()`` makes, which travels to the GPU box).  The ``-m gpu`` tests
+and ``smoke()`` never call it; ``bench.py`` does so only for its CPU arm (``--impl reference`` / ``cpu_baseline``).
 """
 from __future__ import annotations
 
@@ -23,7 +24,10 @@ import os
 import sys
 import types
 
-REF_SRC_CANDIDATES = [os.environ.get("REF_SRC", ""), "/root/reference/src"]
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# /root/reference exists in the build container only; __graft_entry__.build() stages the unmodified sources under
+# baseline/_ref/src (git-ignored, travels to the GPU box with the snapshot) for bench.py's CPU arm
+REF_SRC_CANDIDATES = [os.environ.get("REF_SRC", ""), "/root/reference/src", os.path.join(_REPO, "baseline", "_ref", "src")]
 
 _state = {"module": None, "tickers": []}
 
