@@ -16,9 +16,13 @@ prices already resident in HBM; ``e2e`` times the public host-buffer API includi
 copy of the market and the device->host read of the weights.  N > 1 GPUs: weak scaling, one
 independent synthetic path per rank (BASELINE configs[4]), weights all-gathered with NCCL.
 
-``--impl reference`` times the CPU oracle port (oracle/bayes_oracle.py, the NumPy restatement of the
-reference's algorithm; the reference itself is pandas code that cannot travel to the GPU box) on a
-bounded sample of the same windows with every host core.
+``--impl reference`` times the UNMODIFIED reference (its sources staged under baseline/_ref/src by
+``__graft_entry__.build()``, imported through oracle/ref_import.py, driven one window at a time by
+oracle/ref_runner.py exactly as SURVEY 8(c)/(d) prescribes) on a bounded sample of the same windows with
+every host core (level L0-mp of BASELINE.md section 3: one worker process per core, one BLAS thread each);
+L0 (one process, default BLAS threads), L1 (``backtest_portfolio`` as shipped) and the NumPy port
+(oracle/bayes_oracle.py) are reported beside it.  Only if the staged sources are missing does the arm fall
+back to the port (``kind: "port"``).
 """
 from __future__ import annotations
 
@@ -162,55 +166,146 @@ _G = {}
 
 
 def _ref_window(job):
-    from oracle import bayes_oracle as bo
+    """One window on one worker: the unmodified reference (kind 'reference') or the NumPy port (kind 'port').
+    Returns the weights in ticker order."""
     kind, d = job
     mkt, conj, jeff, cols, hf_days = _G["mkt"], _G["conj"], _G["jeff"], _G["cols"], _G["hf_days"]
+    if _G["impl"] == "reference":
+        from oracle import ref_runner as rr
+        pc = _G["pc"]
+        if kind == 0:
+            df = rr.conjugate_window(pc, conj, mkt, d, cols, hf_lookback_days=hf_days)
+        else:
+            df = rr.jeffreys_window(pc, jeff, mkt, d, cols)
+        return df["Weight"].reindex(_G["tickers"]).to_numpy()
+    from oracle import bayes_oracle as bo
     if kind == 0:
-        return bo.conjugate_window(conj, mkt, d, cols, hf_lookback_days=hf_days)["weights"][:4]
-    return bo.jeffreys_window(jeff, mkt, d, cols)["weights"][:4]
+        return bo.conjugate_window(conj, mkt, d, cols, hf_lookback_days=hf_days)["weights"]
+    return bo.jeffreys_window(jeff, mkt, d, cols)["weights"]
 
 
-def run_reference(args):
-    """CPU arm: the oracle port on every host core, bounded sample of the same windows per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def _ref_setup(args, mkt, conj, jeff, impl):
+    _G.update(mkt=mkt, conj=conj, jeff=jeff, cols=np.arange(args.n_assets), hf_days=args.hf_days, impl=impl,
+              tickers=[mkt.tickers[c] for c in range(args.n_assets)])
+    if impl == "reference":
+        from oracle.ref_import import load_reference, set_universe
+        _G["pc"] = load_reference(check=False)
+        set_universe(mkt.tickers)
+
+
+def reference_impl():
+    from oracle.ref_import import reference_available
+    return "reference" if reference_available() else "port"
+
+
+def sample_jobs(d_idx, n_windows):
+    n = max(1, n_windows // 2)
+    sel = np.linspace(0, len(d_idx) - 1, n).round().astype(int)
+    sel = np.unique(sel)
+    return sel, [(0, int(d_idx[i])) for i in sel] + [(1, int(d_idx[i])) for i in sel]
+
+
+def host_procs():
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    return max(1, min(cores, 64))
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return int(max([p.get("num_threads", 1) for p in threadpool_info()] or [1]))
+    except Exception:
+        return 1
+
+
+def timed_pool(jobs, procs, repeats=1, warm=0):
+    """jobs through a fork pool of `procs` single-BLAS-thread workers; returns (seconds per pass, results of the last)."""
     import multiprocessing as mp
     try:
         from threadpoolctl import threadpool_limits
     except Exception:
         threadpool_limits = None
-    mkt, conj, jeff, d_idx = make_workload(args, 0)
-    cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 64))
-    per_step = max(2 * procs, args.ref_sample)
-    per_step -= per_step % 2
-    sel = np.linspace(0, len(d_idx) - 1, per_step // 2).round().astype(int)
-    jobs = [(0, int(d_idx[i])) for i in sel] + [(1, int(d_idx[i])) for i in sel]
-    _G.update(mkt=mkt, conj=conj, jeff=jeff, cols=np.arange(args.n_assets), hf_days=args.hf_days)
     ctx = mp.get_context("fork")
-    if threadpool_limits:
-        threadpool_limits(1)          # one BLAS thread per worker process: windows are independent
-    with ctx.Pool(procs) as pool:
-        for _ in range(args.warmup):
-            pool.map(_ref_window, jobs, chunksize=1)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            pool.map(_ref_window, jobs, chunksize=1)
-        dt = (time.perf_counter() - t0) / args.steps
+    lim = threadpool_limits(1) if threadpool_limits else None        # one BLAS thread per worker: windows are independent
+    try:
+        with ctx.Pool(procs) as pool:
+            for _ in range(warm):
+                pool.map(_ref_window, jobs, chunksize=1)
+            t0 = time.perf_counter()
+            for _ in range(repeats):
+                res = pool.map(_ref_window, jobs, chunksize=1)
+            dt = (time.perf_counter() - t0) / repeats
+    finally:
+        if lim is not None:
+            lim.restore_original_limits()
+    return dt, res
+
+
+def reference_levels(args, mkt, conj, jeff, d_idx, l0_windows=32, l1_dates=3):
+    """BASELINE.md section 3 beside the headline CPU figure: L0 (weight-function level, ONE process, NumPy's default
+    BLAS threads, CHECK=False), L1 (``backtest_portfolio`` as shipped, CHECK=True, full market_data; the reference's
+    own 1-day intraday look-back) and the NumPy port at L0.  Bounded samples; the reference must be importable."""
+    from oracle import bayes_oracle as bo
+    from oracle import ref_runner as rr
+    out = {}
+    sel, jobs = sample_jobs(d_idx, l0_windows)
+    _ref_setup(args, mkt, conj, jeff, "reference")
+    t0 = time.perf_counter()
+    for j in jobs:
+        _ref_window(j)
+    out["L0"] = {"windows_per_s": len(jobs) / (time.perf_counter() - t0), "windows": len(jobs), "processes": 1,
+                 "blas_threads": blas_threads(), "what": "calculate_conjugate_hf_mcm_portfolio / calculate_jeffreys_portfolio "
+                 "of the unmodified reference on minimal frames, CHECK=False"}
+    _G["impl"] = "port"
+    t0 = time.perf_counter()
+    for j in jobs:
+        _ref_window(j)
+    out["port_L0"] = {"windows_per_s": len(jobs) / (time.perf_counter() - t0), "windows": len(jobs), "processes": 1,
+                      "blas_threads": blas_threads(), "what": "oracle/bayes_oracle.py (NumPy restatement)"}
+    _G["impl"] = "reference"
+    if l1_dates > 0:
+        dd = d_idx[len(d_idx) // 2: len(d_idx) // 2 + l1_dates]
+        sec, reb = rr.loop_level(mkt, conj, dd, check=True)
+        out["L1"] = {"windows_per_s": reb / sec, "windows": int(reb), "processes": 1, "blas_threads": blas_threads(),
+                     "what": "backtest_portfolio as shipped (CHECK=True, universe selection, loop body, 1-day intraday "
+                             "look-back) over consecutive rebalance dates, conjugate strategy"}
+    return out
+
+
+def run_reference(args):
+    """CPU arm: the unmodified reference (L0-mp) on every host core, a bounded sample of the same windows per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mkt, conj, jeff, d_idx = make_workload(args, 0)
+    procs = host_procs()
+    impl = reference_impl()
+    per_step = max(2 * procs, args.ref_sample)
+    sel, jobs = sample_jobs(d_idx, per_step)
+    _ref_setup(args, mkt, conj, jeff, impl)
+    dt, _ = timed_pool(jobs, procs, repeats=args.steps, warm=args.warmup)
     value = len(jobs) / dt
     sample = (f"{len(jobs)} windows per step ({len(jobs)//2} conjugate + {len(jobs)//2} Jeffreys, stratified over the "
-              f"{args.windows} rebalance dates), {procs} worker processes x 1 BLAS thread")
+              f"{args.windows} rebalance dates), {procs} worker processes x 1 BLAS thread (level L0-mp)")
+    cpu = {"value": value, "unit": UNIT, "cores": procs, "kind": impl, "sample": sample}
+    if impl == "reference" and not args.no_levels:
+        cpu["levels"] = reference_levels(args, mkt, conj, jeff, d_idx)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(config_dict(args, 1, conj, jeff, args.hf_days), **intraday_config(mkt, conj, d_idx, args.hf_days)),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "oracle/bayes_oracle.py (NumPy restatement of the reference's algorithm, pinned to the reference's "
-                "outputs by tests/golden); the pandas reference itself cannot travel to the GPU box",
+        "note": ("the UNMODIFIED reference (baseline/_ref/src/portfolio_calculations.py: calculate_conjugate_hf_mcm_portfolio "
+                 ":819-836 with the 7-day look-back through its own calculate_conjugate_prior_S, calculate_jeffreys_portfolio "
+                 ":838-849), CHECK=False, minimal pre-sliced frames (SURVEY 8(c)), NumPy/pandas of this image")
+                if impl == "reference" else
+                "baseline/_ref/src not staged: fell back to oracle/bayes_oracle.py (NumPy restatement pinned by tests/golden)",
     }
     print(json.dumps(line), flush=True)
 
@@ -510,7 +605,7 @@ def run_ours(args):
             "note": "unique work of the backtest (each return row contracted once per phase, one Cholesky + solves per "
                     "window, inputs read once) at the measured DGEMM / HBM peaks, over the measured step"}
         if n_gpus == 1 and not args.no_cpu:
-            line["cpu_baseline"], line["parity_max_rel_err"] = cpu_baseline(args, mkt, conj, jeff, d_idx, out_c, out_j)
+            line["cpu_baseline"], line["parity_max_rel_err"], line["parity"] = cpu_baseline(args, mkt, conj, jeff, d_idx, out_c, out_j)
         if n_gpus == 1 and not args.no_widened:
             line["widened"] = widened_estimators(args, torch, eng, mkt, jeff, d_idx, dgemm_tf, not args.no_cpu)
         print(json.dumps(line), flush=True)
@@ -525,29 +620,44 @@ def eng_ld(N):
 
 
 def cpu_baseline(args, mkt, conj, jeff, d_idx, out_c, out_j):
-    """Oracle port on the box's host cores over a bounded, stratified sample; doubles as a parity check."""
-    from oracle import bayes_oracle as bo
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        threads = 1
-    n = max(2, args.cpu_sample // 2)
-    sel = np.linspace(0, len(d_idx) - 1, n).round().astype(int)
-    cols = np.arange(args.n_assets)
+    """The reference's own CPU path (unmodified sources, level L0-mp: every host core, one BLAS thread per worker)
+    over a bounded, stratified sample of the step's windows; doubles as a parity check of the GPU weights against
+    the unmodified reference AND against the NumPy port.  Falls back to the port alone when baseline/_ref/src is
+    not staged."""
+    procs = host_procs()
+    impl = reference_impl()
     wc = out_c["weights"].cpu().numpy()
     wj = out_j["weights"].cpu().numpy()
-    worst = 0.0
-    t0 = time.perf_counter()
-    for i in sel:
-        r = bo.conjugate_window(conj, mkt, int(d_idx[i]), cols, hf_lookback_days=args.hf_days)["weights"]
-        worst = max(worst, float(np.max(np.abs(wc[i] - r)) / np.max(np.abs(r))))
-        r = bo.jeffreys_window(jeff, mkt, int(d_idx[i]), cols)["weights"]
-        worst = max(worst, float(np.max(np.abs(wj[i] - r)) / np.max(np.abs(r))))
-    dt = time.perf_counter() - t0
-    return ({"value": 2 * n / dt, "unit": UNIT, "cores": int(threads), "kind": "port",
-             "sample": f"{2 * n} windows ({n} conjugate + {n} Jeffreys, stratified over the {len(d_idx)} rebalance dates), "
-                       f"oracle/bayes_oracle.py with NumPy's default BLAS threads ({threads})"}, worst)
+
+    def worst_err(sel, res):
+        n = len(sel)
+        worst = 0.0
+        for k, i in enumerate(sel):
+            for got, ref in ((wc[i], res[k]), (wj[i], res[n + k])):
+                worst = max(worst, float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))))
+        return worst
+
+    parity = {}
+    sel, jobs = sample_jobs(d_idx, args.cpu_sample)
+    _ref_setup(args, mkt, conj, jeff, "port")
+    dt_port, res = timed_pool(jobs, procs)
+    parity["vs_port"] = worst_err(sel, res)
+    port = {"value": len(jobs) / dt_port, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": f"{len(jobs)} windows, oracle/bayes_oracle.py, {procs} worker processes x 1 BLAS thread"}
+    if impl != "reference":
+        return port, parity["vs_port"], parity
+    sel, jobs = sample_jobs(d_idx, args.cpu_sample)
+    _ref_setup(args, mkt, conj, jeff, "reference")
+    dt, res = timed_pool(jobs, procs)
+    parity["vs_reference"] = worst_err(sel, res)
+    cpu = {"value": len(jobs) / dt, "unit": UNIT, "cores": procs, "kind": "reference",
+           "sample": f"{len(jobs)} windows ({len(jobs)//2} conjugate + {len(jobs)//2} Jeffreys, stratified over the "
+                     f"{len(d_idx)} rebalance dates), the unmodified reference (baseline/_ref/src) at level L0-mp: "
+                     f"{procs} worker processes x 1 BLAS thread",
+           "port": port}
+    if not args.no_levels:
+        cpu["levels"] = reference_levels(args, mkt, conj, jeff, d_idx)
+    return cpu, max(parity.values()), parity
 
 
 def widened_estimators(args, torch, eng, mkt, jeff, d_idx, dgemm_tf, with_cpu):
@@ -619,6 +729,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1024, help="windows of the in-run CPU baseline / parity check (~10 s)")
     ap.add_argument("--ref-sample", type=int, default=1024, help="windows per step of the --impl reference arm (~2 s per step)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-levels", action="store_true", help="skip the L0 / L1 / port side measurements of the CPU arm")
     ap.add_argument("--no-widened", action="store_true", help="skip the Jorion / shrinkage measurements (SURVEY 8(f))")
     args = ap.parse_args()
     if args.impl == "reference":
