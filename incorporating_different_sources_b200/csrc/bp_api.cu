@@ -1521,7 +1521,11 @@ int bp_set_upload_fractions(bp_handle* h, int n, const double* cum_fractions) {
     return BP_OK;
 }
 
-int bp_solve_wave_windows(bp_handle* h) { return h ? chol_wave_windows(h->sm_count) : 0; }
+int bp_solve_wave_windows(bp_handle* h) {
+    if (!h) return 0;
+    if (cudaSetDevice(h->device) != cudaSuccess) return 0;      // the cluster occupancy query needs the handle's device
+    return chol_wave_windows(h->sm_count);
+}
 
 int bp_set_stage_timing(bp_handle* h, int enable) {
     if (!h) return fail(BP_ERR_INVALID, "null handle");

@@ -148,8 +148,7 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
     // 1024-byte alignment by pointer arithmetic on the shared array (keeps the shared address space)
     unsigned char* stage_mem = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
     double* P = reinterpret_cast<double*>(stage_mem + CH_STAGES * CH_STAGE_BYTES);   // [32][LDQ]: L_d (lower) + inv(L_d)' (upper)
-    double* red = P + NB * LDQ;            // [NRHS][CH_WARPS][32]
-    double* scratch = red + NRHS * CH_WARPS * NB; // [40]
+    double* scratch = P + NB * LDQ;        // [40]
     // solution vectors of the back substitution: alias the TMA stages (after the last panel they are idle)
     double* xs = reinterpret_cast<double*>(stage_mem);   // [NRHS][Nr]
 
@@ -384,35 +383,14 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
         }
         const double v1 = block_sum(zz, scratch);
 
-        // ---------------- back substitution  L' x = z, panels in reverse (warp r finishes right-hand side r)
-        for (int j0 = Nr - NB; j0 >= 0; j0 -= NB) {
-            double part[NRHS];
-#pragma unroll
-            for (int r = 0; r < NRHS; ++r) part[r] = 0.0;
-            const int col = j0 + lane;
-            if (col < N) {
-                int i = j0 + NB + warp;
-                for (; i + 3 * CH_WARPS < N; i += 4 * CH_WARPS) {        // 4 independent loads in flight
-                    const double s0 = S[(long long)i * ld + col], s1 = S[(long long)(i + CH_WARPS) * ld + col];
-                    const double s2 = S[(long long)(i + 2 * CH_WARPS) * ld + col], s3 = S[(long long)(i + 3 * CH_WARPS) * ld + col];
-#pragma unroll
-                    for (int r = 0; r < NRHS; ++r) {
-                        part[r] = fma(s0, xs[r * Nr + i], part[r]);
-                        part[r] = fma(s1, xs[r * Nr + i + CH_WARPS], part[r]);
-                        part[r] = fma(s2, xs[r * Nr + i + 2 * CH_WARPS], part[r]);
-                        part[r] = fma(s3, xs[r * Nr + i + 3 * CH_WARPS], part[r]);
-                    }
-                }
-                for (; i < N; i += CH_WARPS) {
-                    const double sv = S[(long long)i * ld + col];
-#pragma unroll
-                    for (int r = 0; r < NRHS; ++r) part[r] = fma(sv, xs[r * Nr + i], part[r]);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < NRHS; ++r) red[(r * CH_WARPS + warp) * NB + lane] = part[r];
+        // ---------------- back substitution  L' x = z, right-looking over 32-column blocks, in place in xs: block b is
+        // solved (warp r finishes right-hand side r), then every block bb < b is reduced by L[rows of b, columns of bb]' x_b
+        // (one warp per block, coalesced rows).  Operation for operation the arithmetic of chol_cluster.cu, so that a
+        // batch gives bit-identical weights however its windows are split over launches and kernels.
+        for (int b = Nr / NB - 1; b >= 0; --b) {
+            const int j0 = NB * b;
             for (int i = warp; i < NB; i += CH_WARPS) {
-                const int row = j0 + i;
+                const int row = j0 + i, col = j0 + lane;
                 double v;
                 if (row < N && col < N) v = lane <= i ? S[(long long)row * ld + col] : 0.0;
                 else v = i == lane ? 1.0 : 0.0;
@@ -420,10 +398,7 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
             }
             __syncthreads();
             if (warp < NRHS) {
-                double* xr = xs + warp * Nr;
-                double r = xr[col];
-#pragma unroll
-                for (int wv = 0; wv < CH_WARPS; ++wv) r -= red[(warp * CH_WARPS + wv) * NB + lane];
+                double r = xs[warp * Nr + j0 + lane];
                 const double rd = 1.0 / P[lane * LDQ + lane];      // all 32 reciprocals in parallel
 #pragma unroll
                 for (int k = NB - 1; k >= 0; --k) {
@@ -431,10 +406,34 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
                     if (lane == k) r = xk;
                     if (lane < k) r = fma(-P[k * LDQ + lane], xk, r);
                 }
-                xr[col] = r;
+                xs[warp * Nr + j0 + lane] = r;
             }
             __syncthreads();
+            const int rows = min(NB, N - j0);
+            for (int bb = warp; bb < b; bb += CH_WARPS) {
+                const int col = NB * bb + lane;
+                double a0[NRHS], a1[NRHS];
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) a0[r] = a1[r] = 0.0;
+#pragma unroll 4
+                for (int i = 0; i + 1 < rows; i += 2) {
+                    const double l0 = S[(long long)(j0 + i) * ld + col], l1 = S[(long long)(j0 + i + 1) * ld + col];
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) {
+                        a0[r] = fma(l0, xs[r * Nr + j0 + i], a0[r]);
+                        a1[r] = fma(l1, xs[r * Nr + j0 + i + 1], a1[r]);
+                    }
+                }
+                if (rows & 1) {
+                    const double l0 = S[(long long)(j0 + rows - 1) * ld + col];
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r) a0[r] = fma(l0, xs[r * Nr + j0 + rows - 1], a0[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r) xs[r * Nr + col] -= a0[r] + a1[r];
+            }
         }
+        __syncthreads();
 
         PROF(3)
         // ---------------- posterior scalars and weights
@@ -510,11 +509,17 @@ size_t chol_smem_bytes(int n_assets, int nrhs) {
     const int Nr = (n_assets + NB - 1) / NB * NB;
     // xs aliases the stage ring: it must hold it
     if ((size_t)CH_STAGES * CH_STAGE_BYTES < sizeof(double) * (size_t)Nr * nrhs) return 0;
-    return (size_t)CH_TMA_SMEM + sizeof(double) * (size_t)(NB * LDQ + nrhs * CH_WARPS * NB + 40);
+    return (size_t)CH_TMA_SMEM + sizeof(double) * (size_t)(NB * LDQ + 40);
 }
 
 cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int sm_count, cudaStream_t st) {
     if (p.n_windows <= 0) return cudaSuccess;
+    static const bool profile = getenv("BP_CHOL_PROFILE") != nullptr;
+    if (!profile) {
+        // launches too small to fill the machine: one thread-block cluster per window (chol_cluster.cu)
+        const cudaError_t ec = launch_chol_cluster(p, smap, chol_wave_windows(sm_count), st);
+        if (ec != cudaErrorNotSupported) return ec;
+    }
     const int nrhs = p.estimator == BP_EST_JORION ? 2 : 1;
     const size_t smem = chol_smem_bytes(p.n_assets, nrhs);
     if (smem == 0) return cudaErrorInvalidValue;      // N too large for the aliased back-substitution vector
@@ -527,7 +532,6 @@ cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int
         chol_solve_kernel<2><<<grid, CH_THREADS, smem, st>>>(smap, p);
         return cudaGetLastError();
     }
-    static const bool profile = getenv("BP_CHOL_PROFILE") != nullptr;
     if (profile) {
         SolveParams q = p;
         static long long* dbg = nullptr;

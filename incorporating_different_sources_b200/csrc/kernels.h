@@ -270,5 +270,9 @@ int chain_max_group();
 cudaError_t launch_jeffreys_chain(const ChainParams& p, cudaStream_t st);
 cudaError_t launch_chol_solve(const SolveParams& p, const CUtensorMap& smap, int sm_count, cudaStream_t st);
 int chol_wave_windows(int sm_count);
+// chol_cluster.cu: one thread-block cluster of K CTAs per window for launches of fewer than cta_slots / 2 windows (K =
+// 8, 4 or 2, the largest with n_windows * K <= cta_slots); cudaErrorNotSupported otherwise (and when N is too large for
+// the aliased back-substitution vectors, or with BP_CHOL_CLUSTER=0): the caller then runs chol_solve_kernel
+cudaError_t launch_chol_cluster(const SolveParams& p, const CUtensorMap& smap, int cta_slots, cudaStream_t st);
 
 }  // namespace bp
