@@ -70,7 +70,11 @@ def config_dict(args, n_gpus, conj, jeff, hf_days):
         "workload": "C2: full daily-rebalance backtest, conjugate(VIX)+Jeffreys, synthetic S&P-500-sized universe",
         "n_assets": args.n_assets, "rebalance_dates": args.windows, "windows_per_step_per_gpu": 2 * args.windows,
         "conjugate": {"rolling_window": conj["rolling_window"], "hf_lookback_calendar_days": hf_days,
-                      "hf_bar_minutes": 5, "prior": "vw", "mcm": "VIX"},
+                      "hf_bar_minutes": 5, "prior": "vw", "mcm": "VIX",
+                      "hf_lookback_note": "SURVEY 8(d) asks for an injected look-back >= 5 days at N=500 (the reference's own "
+                                          "1-day window is rank deficient, F6); 7 calendar days is the shortest one in the "
+                                          "reference's table (:299-304); --hf-days 366 (252 trading days) costs 1.1x this step "
+                                          "(profiles/r2*_bench_hf366.json)"},
         "jeffreys": {"rolling_window": jeff["rolling_window"]},
         "sharding": f"{n_gpus} independent synthetic path(s), one per GPU; weights all-gathered (NCCL)" if n_gpus > 1
         else "single GPU, one path",
@@ -500,6 +504,21 @@ def run_ours(args):
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     e2e_value = n_gpus * 2 * W / e2e_s
     e2e_match = bool(np.array_equal(hw_cv, out_c["weights"].cpu().numpy()))
+    # platform limit of the e2e leg: every rank copies a buffer of its intraday block's size at once (plain cudaMemcpyAsync)
+    hf_t = keep[2]
+    torch.cuda.synchronize()
+    dst = torch.empty(hf_t.shape, dtype=torch.float64, device=dev)
+    dst.copy_(hf_t, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        dst.copy_(hf_t, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_s = max_over_ranks((time.perf_counter() - t0) / 3)
+    del dst
+    h2d_ceiling = {"bytes_per_rank": int(hf_t.numel() * 8), "ranks": world, "ms": h2d_s * 1e3,
+                   "per_rank_gbs": hf_t.numel() * 8 / h2d_s / 1e9, "aggregate_gbs": world * hf_t.numel() * 8 / h2d_s / 1e9,
+                   "what": "pinned -> device cudaMemcpyAsync of the intraday block alone, all ranks at once, max over ranks"}
 
     if rank == 0:
         work = algorithmic_work(N, W, conj["rolling_window"], m_hf, jeff["rolling_window"])
@@ -573,7 +592,11 @@ def run_ours(args):
                            **intraday_config(mkt, conj, d_idx, args.hf_days)),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_s * 1e3, "matches_device_path": e2e_match},
+                    "ms_per_step": e2e_s * 1e3, "matches_device_path": e2e_match, "steps": e2e_steps,
+                    "inputs": "host buffers pinned once outside the timed region; windows planned once outside it",
+                    "h2d_ceiling": h2d_ceiling,
+                    "h2d_ms_at_ceiling": h2d_bytes / (h2d_ceiling["per_rank_gbs"] * 1e9) * 1e3,
+                    "frac_of_h2d_ceiling": (h2d_bytes / (h2d_ceiling["per_rank_gbs"] * 1e9)) / e2e_s},
             "gpu_launches": int(launches),
             "roofline": dominant,
             "stages": {
@@ -731,9 +754,18 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-levels", action="store_true", help="skip the L0 / L1 / port side measurements of the CPU arm")
     ap.add_argument("--no-widened", action="store_true", help="skip the Jorion / shrinkage measurements (SURVEY 8(f))")
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5"],
+                    help="BASELINE.json configuration (default C2 = the headline metric); see bench_configs.py")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one independent path per GPU; strong = ONE backtest split by date range (north star)")
+    ap.add_argument("--paths", type=int, default=64, help="C5: independent synthetic paths in total")
+    ap.add_argument("--path-pool", type=int, default=2, help="C5: distinct generated markets per GPU the paths cycle through")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "C2" or args.scaling == "strong":
+        import bench_configs
+        bench_configs.dispatch(args)
     else:
         run_ours(args)
 

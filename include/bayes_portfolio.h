@@ -131,6 +131,10 @@ int bp_destroy(bp_handle* h);
 /* Launch on the caller's CUDA stream (a cudaStream_t), e.g. torch's current stream. */
 int bp_set_stream(bp_handle* h, void* cuda_stream);
 int bp_synchronize(bp_handle* h);
+/* Block the calling host thread until the intraday block of the last bp_upload_market_async has arrived in HBM (kernels
+ * queued behind it may still be running).  Lets a caller that alternates between two handles start the upload of the
+ * next market when the link is free instead of sharing it between two transfers (bench_configs.py, C5). */
+int bp_wait_upload(bp_handle* h);
 /* With enable != 0 the batched calls return as soon as their work is queued even when the outputs are HOST
  * buffers (which must then be page-locked): the results are complete after bp_synchronize().  Lets the host
  * plan the next batch (e.g. the conjugate windows) while the GPU still works on the previous one (Jeffreys).

@@ -1427,6 +1427,13 @@ int bp_synchronize(bp_handle* h) {
     return BP_OK;
 }
 
+int bp_wait_upload(bp_handle* h) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    CU_TRY(cudaSetDevice(h->device));
+    if (h->has_market && h->R > 0) CU_TRY(cudaEventSynchronize(h->ev_hf));      // the intraday block (copy stream)
+    return BP_OK;
+}
+
 int bp_set_async_outputs(bp_handle* h, int enable) {
     if (!h) return fail(BP_ERR_INVALID, "null handle");
     if (!enable && h->need_sync) {

@@ -46,7 +46,7 @@ class BayesEngine:
         ``torch.distributed`` collectives order correctly with the kernels.
     """
 
-    def __init__(self, device: int = 0, use_torch_stream: bool = True):
+    def __init__(self, device: int = 0, use_torch_stream: bool = True, stream=None):
         self._lib = _lib.load()
         h = C.c_void_p()
         rc = self._lib.bp_init(int(device), C.byref(h))
@@ -58,7 +58,8 @@ class BayesEngine:
         self.n_days = 0
         self.n_hf_rows = 0
         self._torch = None
-        if use_torch_stream:
+        self._stream = stream        # a torch.cuda.Stream of this engine's own (two engines then overlap on one GPU)
+        if use_torch_stream or stream is not None:
             import torch
             self._torch = torch
             torch.cuda.set_device(self.device)
@@ -67,7 +68,7 @@ class BayesEngine:
     # ------------------------------------------------------------------ plumbing
     def bind_torch_stream(self):
         torch = self._torch
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = (self._stream if self._stream is not None else torch.cuda.current_stream(self.device)).cuda_stream
         rc = self._lib.bp_set_stream(self._h, C.c_void_p(stream))
         if rc:
             _raise(rc)
@@ -88,6 +89,12 @@ class BayesEngine:
         if rc:
             _raise(rc)
         self._inflight = None
+
+    def wait_upload(self):
+        """Block until the intraday block of the last asynchronous ``upload_market`` has arrived in HBM."""
+        rc = self._lib.bp_wait_upload(self._h)
+        if rc:
+            _raise(rc)
 
     def set_workspace_limit(self, nbytes: int):
         rc = self._lib.bp_set_workspace_limit(self._h, C.c_size_t(int(nbytes)))

@@ -159,17 +159,27 @@ class ShardedBacktest:
         self.gamma_j = float(jeff_spec["risk_aversion"])
         self.cost = float(conj_spec["turnover_cost"])
         self.n_assets = mkt.n_assets
+        self._fractions = None
 
     def upload(self, async_copy: bool = False):
+        """Host slice -> HBM.  ``async_copy`` (page-locked host arrays, see ``pin``): the intraday block travels in
+        wave-aligned segments on the copy stream, so that :meth:`compute` overlaps it (Jeffreys does not read intraday
+        data; the conjugate stages run on the segments that have arrived)."""
+        if async_copy:
+            if self._fractions is None:
+                self._fractions = self.engine.plan_upload_fractions(self.cb, self.host["hf_prices"].shape[0])
+            self.engine.set_upload_fractions(self._fractions)
         self.engine.upload_market(**self.host, async_copy=async_copy)
+        if async_copy:
+            self.engine.set_upload_fractions(None)
 
     def compute(self, out_c, out_j, loop: bool = True):
         """Weights of the shard's windows into ``out_c`` / ``out_j`` (dicts with 'weights' [n_ext][N] and 'status'
         CUDA tensors) and, with ``loop``, the loop body of both strategies.  Returns the local rows to gather:
         (weights_c, weights_j, returns_c, returns_j, turnover_c, turnover_j) without the halo window."""
         eng = self.engine
+        eng.jeffreys(self.jb, outputs=("weights", "status"), into=out_j)      # first: needs no intraday data
         eng.conjugate(self.cb, outputs=("weights", "status"), into=out_c)
-        eng.jeffreys(self.jb, outputs=("weights", "status"), into=out_j)
         k = self.halo
         res = [out_c["weights"][k:], out_j["weights"][k:]]
         if loop:
