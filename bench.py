@@ -631,11 +631,42 @@ def run_ours(args):
             line["cpu_baseline"], line["parity_max_rel_err"], line["parity"] = cpu_baseline(args, mkt, conj, jeff, d_idx, out_c, out_j)
         if n_gpus == 1 and not args.no_widened:
             line["widened"] = widened_estimators(args, torch, eng, mkt, jeff, d_idx, dgemm_tf, not args.no_cpu)
+        if n_gpus == 1 and not args.no_loop:
+            line["loop_e2e"] = loop_level(args, eng, mkt, conj, jeff, d_idx)
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def loop_level(args, eng, mkt, conj, jeff, d_idx):
+    """SURVEY 8(f) ranks 1-2, OUTSIDE the timed region of the headline metric: the reference's loop-level entry point
+    ``backtest_portfolio(portfolio_spec, ts_start_date, ts_end_date, market_data)`` (:1221-1238) on pandas frames, whole
+    backtest, wall clock: calendar, universe selection for every date (vectorised, :611-658), ONE upload of the market
+    into the resident pool, device gathers per asset set, batched weights, loop-body kernel, pandas containers out.
+    The reference's own loop (level L1 of the CPU arm) is the figure to set beside it."""
+    import pandas as pd
+    from incorporating_different_sources_b200 import portfolio_calculations as pcg
+    md = mkt.market_data()                      # the 10-key dict of data_handling.py:282-291 (input boundary, not timed)
+    start, end = pd.Timestamp(mkt.dates[d_idx[0]]), pd.Timestamp(mkt.dates[d_idx[-1]])
+    out = {"entry_point": "backtest_portfolio(spec, start, end, market_data) with pandas frames, wall clock, everything inside",
+           "n_assets": args.n_assets, "rebalance_dates": int(len(d_idx))}
+    for name, spec, kw in (("jeffreys", jeff, {}), ("conjugate", conj, {"hf_lookback_days": args.hf_days})):
+        best = None
+        for _ in range(2):                      # second pass: allocations of the first one are reused
+            tm = {}
+            t0 = time.perf_counter()
+            res = pcg.backtest_portfolio(spec, start, end, md, engine=eng, timings=tm, **kw)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best["seconds"]:
+                r = res["portfolio_simple_returns_series"].to_numpy()
+                best = dict(seconds=dt, windows_per_s=len(d_idx) / dt, phases_s={k: v for k, v in tm.items() if k.endswith("_s")},
+                            asset_sets=tm.get("asset_sets"), returns=int(len(r)), returns_finite=bool(np.isfinite(r).all()),
+                            turnover_rows=int(len(res["portfolio_turnover_series"])),
+                            metrics_shape=list(res["portfolio_weights_metrics_df"].shape))
+        out[name] = best
+    return out
 
 
 def eng_ld(N):
@@ -753,6 +784,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=1024, help="windows per step of the --impl reference arm (~2 s per step)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-levels", action="store_true", help="skip the L0 / L1 / port side measurements of the CPU arm")
+    ap.add_argument("--no-loop", action="store_true", help="skip the loop-level (backtest_portfolio) measurement (SURVEY 8(f))")
     ap.add_argument("--no-widened", action="store_true", help="skip the Jorion / shrinkage measurements (SURVEY 8(f))")
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5"],
                     help="BASELINE.json configuration (default C2 = the headline metric); see bench_configs.py")

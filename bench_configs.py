@@ -218,7 +218,7 @@ def run_strong(args):
     torch.cuda.synchronize()
     stages = stage_ms(eng, 1)
     gwork, swork = eng.gram_work(), eng.solve_work()
-    launches = eng.launch_count - l0 + (6 if ctx.world > 1 else 0)
+    launches = eng.launch_count - l0 + (1 if ctx.world > 1 else 0)      # + the one all-gather
     eng.set_stage_timing(False)
     bad = ctx.sum_over_ranks(float((out_c["status"] != 0).sum().item() + (out_j["status"] != 0).sum().item()))
 

@@ -199,6 +199,19 @@ int bp_upload_market(bp_handle* h, const bp_market_desc* m);
  * valid until bp_synchronize().  The intraday block travels on a second stream, so a following
  * bp_jeffreys_batched / bp_stats_batched overlaps the transfer; conjugate calls wait for it. */
 int bp_upload_market_async(bp_handle* h, const bp_market_desc* m);
+/* Loop level (calculate_portfolio_weights, :954-988, slices the frames to the universe of EACH date; backtest_portfolio,
+ * :1221-1238, does so once per trading day): the full market -- every candidate column, every row -- is uploaded ONCE
+ * into a resident pool, and the working market of a batch (the universe of a run of dates in cap-descending order, the
+ * rows its windows read) is gathered from it on the device: no host -> device transfer per asset set.
+ * bp_upload_pool(h, NULL) releases the pool. */
+int bp_upload_pool(bp_handle* h, const bp_market_desc* m);
+typedef struct bp_pool_select {
+    int n_cols;
+    const int* cols;        /* pool columns, in the order they take in the working market */
+    int day_lo, day_hi;     /* daily rows [day_lo, day_hi) of the pool */
+    long long hf_lo, hf_hi; /* intraday rows [hf_lo, hf_hi) (equal: none) */
+} bp_pool_select;
+int bp_select_market(bp_handle* h, const bp_pool_select* s);
 /* Re-run the log-return stage on the resident prices (device-only timing of the whole path). */
 int bp_prepare_market(bp_handle* h);
 

@@ -28,7 +28,7 @@ EXPORTED = [
     "bp_excess_returns", "bp_quadratic_form", "bp_dense_posterior", "bp_moments_batched",
     "bp_upload_market_async", "bp_backtest_batched", "bp_get_gram_work", "bp_set_reuse_min_windows", "bp_set_upload_pipeline", "bp_set_async_outputs",
     "bp_set_resampled", "bp_estimator_batched", "bp_set_jeffreys_chain", "bp_get_solve_work",
-    "bp_set_upload_fractions", "bp_solve_wave_windows", "bp_set_hf_presum_min_days", "bp_wait_upload",
+    "bp_set_upload_fractions", "bp_solve_wave_windows", "bp_set_hf_presum_min_days", "bp_wait_upload", "bp_upload_pool", "bp_select_market",
 ]
 BP_NSTAGE = 8
 STAGES = ("logret", "prep", "gram", "solve", "chain")
@@ -93,6 +93,11 @@ class LibraryMissing(RuntimeError):
 _lib = None
 
 
+class PoolSelect(C.Structure):
+    _fields_ = [("n_cols", C.c_int), ("cols", C.c_void_p), ("day_lo", C.c_int), ("day_hi", C.c_int),
+                ("hf_lo", C.c_longlong), ("hf_hi", C.c_longlong)]
+
+
 def load():
     """Load the shared library (building is the job of ``__graft_entry__.build()``)."""
     global _lib
@@ -110,6 +115,8 @@ def load():
     lib.bp_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.bp_synchronize.argtypes = [C.c_void_p]
     lib.bp_wait_upload.argtypes = [C.c_void_p]
+    lib.bp_upload_pool.argtypes = [C.c_void_p, C.POINTER(MarketDesc)]
+    lib.bp_select_market.argtypes = [C.c_void_p, C.POINTER(PoolSelect)]
     lib.bp_set_workspace_limit.argtypes = [C.c_void_p, C.c_size_t]
     lib.bp_device_info.argtypes = [C.c_void_p, c_int_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.bp_launch_count.argtypes = [C.c_void_p]

@@ -70,6 +70,13 @@ struct bp_handle {
     double *prices = nullptr, *lr_d = nullptr, *caps = nullptr, *hf_prices = nullptr, *lr_hf = nullptr,
            *mcm = nullptr, *rf_row = nullptr;
     bool has_caps = false;
+    // resident POOL: the full market (every column, every row) kept in HBM so that the working market of a batch
+    // (a column subset in a given order, a row range) is gathered on the device instead of uploaded again
+    double *pool_prices = nullptr, *pool_caps = nullptr, *pool_hf = nullptr, *pool_rf = nullptr;
+    int pool_N = 0, pool_D = 0;
+    long long pool_R = 0;
+    int* pool_cols = nullptr;
+    size_t pool_cols_cap = 0;
     // resampled (weekly) return rows: see bp_set_resampled
     double *lr_w = nullptr, *rf_w = nullptr, *mcm_w = nullptr;
     int* rs_idx = nullptr;
@@ -181,6 +188,13 @@ void free_resampled(bp_handle* h) {
     h->lr_w = h->rf_w = h->mcm_w = nullptr;
     h->rs_idx = nullptr;
     h->Rw = 0;
+}
+
+void free_pool(bp_handle* h) {
+    cudaFree(h->pool_prices); cudaFree(h->pool_caps); cudaFree(h->pool_hf); cudaFree(h->pool_rf);
+    h->pool_prices = h->pool_caps = h->pool_hf = h->pool_rf = nullptr;
+    h->pool_N = h->pool_D = 0;
+    h->pool_R = 0;
 }
 
 void free_market(bp_handle* h) {
@@ -1379,6 +1393,8 @@ int bp_destroy(bp_handle* h) {
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
     free_market(h);
+    free_pool(h);
+    cudaFree(h->pool_cols);
     cudaStreamDestroy(h->copy_stream);
     cudaEventDestroy(h->ev_main);
     cudaEventDestroy(h->ev_hf);
@@ -1589,17 +1605,11 @@ int bp_prepare_market(bp_handle* h) {
 // copies (full PCIe rate from pinned memory) and padded on the fly by the log-return kernel.  The
 // intraday block (by far the largest) goes over a second stream together with its log-return kernel,
 // so stages that do not read it (Jeffreys, daily statistics) overlap the transfer.
-static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocking) {
-    if (!h || !m) return fail(BP_ERR_INVALID, "null handle or market");
-    if (m->n_assets <= 0 || m->n_days < 2 || !m->prices || !m->rf_row)
-        return fail(BP_ERR_INVALID, "market needs n_assets > 0, n_days >= 2, prices and rf_row");
-    if (m->n_hf_rows < 0 || (m->n_hf_rows > 0 && !m->hf_prices)) return fail(BP_ERR_INVALID, "hf_prices missing");
-    if (m->n_hf_rows > 0x7fffffffLL) return fail(BP_ERR_INVALID, "too many intraday rows for int32 row indices");
-    if (m->n_mcm < 0 || (m->n_mcm > 0 && !m->mcm)) return fail(BP_ERR_INVALID, "mcm missing");
-    CU_TRY(cudaSetDevice(h->device));
-    const int N = m->n_assets, D = m->n_days, ld = round_up(N, 16);
-    const long long R = m->n_hf_rows;
-    const size_t need_daily = (size_t)D * ld, need_hf = (size_t)R * ld, need_mcm = (size_t)std::max(m->n_mcm, 1) * D;
+// Working-market buffers for N columns, D daily rows, R intraday rows (grown when needed) and the bookkeeping every
+// way of filling them shares (host upload, device gather from the pool)
+static int begin_market(bp_handle* h, int N, int D, long long R, int n_mcm) {
+    const int ld = round_up(N, 16);
+    const size_t need_daily = (size_t)D * ld, need_hf = (size_t)R * ld, need_mcm = (size_t)std::max(n_mcm, 1) * D;
     if (need_daily > h->cap_daily || need_hf > h->cap_hf || need_mcm > h->cap_mcm || (size_t)D > h->cap_days) {
         // grow: everything in flight must be done with the old buffers
         CU_TRY(cudaStreamSynchronize(h->stream));
@@ -1626,18 +1636,57 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
         CU_TRY(cudaStreamSynchronize(h->stream));
         free_resampled(h);
     }
-    h->N = N; h->D = D; h->ld = ld; h->R = R; h->n_mcm = m->n_mcm;
-    h->has_caps = m->caps != nullptr;
-    cudaStream_t st = h->stream;
+    h->N = N; h->D = D; h->ld = ld; h->R = R; h->n_mcm = n_mcm;
     if (h->timing) {
         if (!h->ev_t0) CU_TRY(cudaEventCreate(&h->ev_t0));
-        CU_TRY(cudaEventRecord(h->ev_t0, st));
+        CU_TRY(cudaEventRecord(h->ev_t0, h->stream));
         h->t0_armed = true;
     }
+    h->n_seg = 0;
+    h->seg_waited = 0;
+    h->lr_hf_done = 0;
+    h->hf_pending = false;
+    return BP_OK;
+}
+
+// daily log returns and the tensor maps of the (filled or being filled) working market
+static int finish_market(bp_handle* h) {
+    const int N = h->N, D = h->D, ld = h->ld;
+    const long long R = h->R;
+    int rc;
+    launch_log_returns(h->prices, N, h->lr_d, ld, D, N, h->sm_count, h->stream);
+    h->launches++;
+    CU_TRY(cudaGetLastError());
+    if ((rc = make_map(h, &h->map_d, h->lr_d, D, ld))) return rc;
+    if (R > 0) {
+        // rows available behind the R return rows at the CURRENT leading dimension
+        h->hf_extra_rows = (long long)((size_t)h->lr_hf_rows_cap * h->lr_hf_ld_cap / ld) - R;
+        if (h->hf_extra_rows < 0) h->hf_extra_rows = 0;
+        if ((rc = make_map(h, &h->map_hf, h->lr_hf, R + h->hf_extra_rows, ld))) return rc;
+    } else {
+        h->map_hf = h->map_d;
+    }
+    h->has_market = true;
+    return BP_OK;
+}
+
+static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocking) {
+    if (!h || !m) return fail(BP_ERR_INVALID, "null handle or market");
+    if (m->n_assets <= 0 || m->n_days < 2 || !m->prices || !m->rf_row)
+        return fail(BP_ERR_INVALID, "market needs n_assets > 0, n_days >= 2, prices and rf_row");
+    if (m->n_hf_rows < 0 || (m->n_hf_rows > 0 && !m->hf_prices)) return fail(BP_ERR_INVALID, "hf_prices missing");
+    if (m->n_hf_rows > 0x7fffffffLL) return fail(BP_ERR_INVALID, "too many intraday rows for int32 row indices");
+    if (m->n_mcm < 0 || (m->n_mcm > 0 && !m->mcm)) return fail(BP_ERR_INVALID, "mcm missing");
+    CU_TRY(cudaSetDevice(h->device));
+    const int N = m->n_assets, D = m->n_days;
+    const long long R = m->n_hf_rows;
+    int rc;
+    if ((rc = begin_market(h, N, D, R, m->n_mcm))) return rc;
+    h->has_caps = m->caps != nullptr;
+    cudaStream_t st = h->stream;
     // the copy stream must not overwrite buffers that earlier launches on the compute stream still read
     CU_TRY(cudaEventRecord(h->ev_main, st));
     CU_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_main, 0));
-    int rc;
     // small daily arrays first: both streams share one host->device copy engine, which serves copies in
     // issue order, and the Jeffreys / daily stages must not queue behind the 1.6 GB intraday block
     CU_TRY(cudaMemcpyAsync(h->prices, m->prices, sizeof(double) * (size_t)D * N, cudaMemcpyHostToDevice, st));
@@ -1645,9 +1694,6 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
     if (m->n_mcm > 0)
         CU_TRY(cudaMemcpyAsync(h->mcm, m->mcm, sizeof(double) * (size_t)m->n_mcm * D, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(h->rf_row, m->rf_row, sizeof(double) * (size_t)D, cudaMemcpyHostToDevice, st));
-    h->n_seg = 0;
-    h->seg_waited = 0;
-    h->lr_hf_done = 0;
     if (R > 0) {
         // asynchronous uploads of a large block go in segments with an event each; the log returns of a segment
         // are computed on the compute stream by its first consumer (wait_hf / the pipelined conjugate path)
@@ -1674,25 +1720,90 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
         CU_TRY(cudaEventRecord(h->ev_hf, h->copy_stream));
         h->hf_pending = true;
     }
-    launch_log_returns(h->prices, N, h->lr_d, ld, D, N, h->sm_count, st);
-    h->launches++;
-    CU_TRY(cudaGetLastError());
-    if ((rc = make_map(h, &h->map_d, h->lr_d, D, ld))) return rc;
-    if (R > 0) {
-        // rows available behind the R return rows at the CURRENT leading dimension
-        h->hf_extra_rows = (long long)((size_t)h->lr_hf_rows_cap * h->lr_hf_ld_cap / ld) - R;
-        if (h->hf_extra_rows < 0) h->hf_extra_rows = 0;
-        if ((rc = make_map(h, &h->map_hf, h->lr_hf, R + h->hf_extra_rows, ld))) return rc;
-    } else {
-        h->map_hf = h->map_d;
-    }
-    h->has_market = true;
+    if ((rc = finish_market(h))) return rc;
     if (blocking) {
         // the caller's host arrays may be pageable and may be freed after return
         CU_TRY(cudaStreamSynchronize(h->copy_stream));
         CU_TRY(cudaStreamSynchronize(st));
     }
     return BP_OK;
+}
+
+int bp_upload_pool(bp_handle* h, const bp_market_desc* m) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaStreamSynchronize(h->stream));            // earlier gathers may still read the old pool
+    free_pool(h);
+    if (!m) return BP_OK;                                  // a null market releases the pool
+    if (m->n_assets <= 0 || m->n_days < 2 || !m->prices || !m->rf_row)
+        return fail(BP_ERR_INVALID, "pool needs n_assets > 0, n_days >= 2, prices and rf_row");
+    if (m->n_hf_rows < 0 || (m->n_hf_rows > 0 && !m->hf_prices)) return fail(BP_ERR_INVALID, "hf_prices missing");
+    if (m->n_hf_rows > 0x7fffffffLL) return fail(BP_ERR_INVALID, "too many intraday rows for int32 row indices");
+    const size_t N = (size_t)m->n_assets, D = (size_t)m->n_days, R = (size_t)m->n_hf_rows;
+    cudaStream_t st = h->stream;
+    CU_TRY(cudaMalloc(&h->pool_prices, sizeof(double) * D * N));
+    CU_TRY(cudaMalloc(&h->pool_rf, sizeof(double) * D));
+    CU_TRY(cudaMemcpyAsync(h->pool_prices, m->prices, sizeof(double) * D * N, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(h->pool_rf, m->rf_row, sizeof(double) * D, cudaMemcpyHostToDevice, st));
+    if (m->caps) {
+        CU_TRY(cudaMalloc(&h->pool_caps, sizeof(double) * D * N));
+        CU_TRY(cudaMemcpyAsync(h->pool_caps, m->caps, sizeof(double) * D * N, cudaMemcpyHostToDevice, st));
+    }
+    if (R > 0) {
+        CU_TRY(cudaMalloc(&h->pool_hf, sizeof(double) * R * N));
+        CU_TRY(cudaMemcpyAsync(h->pool_hf, m->hf_prices, sizeof(double) * R * N, cudaMemcpyHostToDevice, st));
+    }
+    CU_TRY(cudaStreamSynchronize(st));                    // the host arrays may be pageable / freed after return
+    h->pool_N = m->n_assets;
+    h->pool_D = m->n_days;
+    h->pool_R = m->n_hf_rows;
+    return BP_OK;
+}
+
+int bp_select_market(bp_handle* h, const bp_pool_select* s) {
+    if (!h || !s) return fail(BP_ERR_INVALID, "null handle or selection");
+    if (!h->pool_prices) return fail(BP_ERR_STATE, "no pool resident: call bp_upload_pool first");
+    if (s->n_cols <= 0 || !s->cols) return fail(BP_ERR_INVALID, "selection needs at least one column");
+    if (s->day_lo < 0 || s->day_hi > h->pool_D || s->day_hi - s->day_lo < 2)
+        return fail(BP_ERR_INVALID, "daily row range [%d, %d) outside the pool's %d rows (or shorter than 2)", s->day_lo, s->day_hi, h->pool_D);
+    if (s->hf_lo < 0 || s->hf_hi < s->hf_lo || s->hf_hi > h->pool_R)
+        return fail(BP_ERR_INVALID, "intraday row range outside the pool");
+    for (int j = 0; j < s->n_cols; ++j)
+        if (s->cols[j] < 0 || s->cols[j] >= h->pool_N) return fail(BP_ERR_INVALID, "column %d outside the pool's %d columns", s->cols[j], h->pool_N);
+    CU_TRY(cudaSetDevice(h->device));
+    const int N = s->n_cols, D = s->day_hi - s->day_lo;
+    const long long R = s->hf_hi - s->hf_lo;
+    int rc;
+    if ((rc = begin_market(h, N, D, R, 0))) return rc;
+    h->has_caps = h->pool_caps != nullptr;
+    cudaStream_t st = h->stream;
+    if ((size_t)N > h->pool_cols_cap) {
+        CU_TRY(cudaStreamSynchronize(st));
+        cudaFree(h->pool_cols);
+        h->pool_cols = nullptr;
+        h->pool_cols_cap = 0;
+        CU_TRY(cudaMalloc(&h->pool_cols, sizeof(int) * (size_t)N));
+        h->pool_cols_cap = (size_t)N;
+    }
+    // (pageable host memory: the copy is staged before the call returns, so the caller's array may go away; stream
+    // order keeps earlier gathers, which read the previous column list, ahead of it)
+    CU_TRY(cudaMemcpyAsync(h->pool_cols, s->cols, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
+    const long long pN = h->pool_N;
+    launch_gather_cols(h->pool_prices + (size_t)s->day_lo * pN, pN, h->prices, N, D, h->pool_cols, h->sm_count, st);
+    h->launches++;
+    if (h->pool_caps) {
+        launch_gather_cols(h->pool_caps + (size_t)s->day_lo * pN, pN, h->caps, N, D, h->pool_cols, h->sm_count, st);
+        h->launches++;
+    }
+    CU_TRY(cudaMemcpyAsync(h->rf_row, h->pool_rf + s->day_lo, sizeof(double) * (size_t)D, cudaMemcpyDeviceToDevice, st));
+    if (R > 0) {
+        launch_gather_cols(h->pool_hf + (size_t)s->hf_lo * pN, pN, h->hf_prices, N, R, h->pool_cols, h->sm_count, st);
+        h->launches++;
+        CU_TRY(cudaEventRecord(h->ev_hf, st));
+        h->hf_pending = true;            // the first consumer computes the intraday log returns (wait_hf)
+    }
+    CU_TRY(cudaGetLastError());
+    return finish_market(h);
 }
 
 int bp_upload_market(bp_handle* h, const bp_market_desc* m) { return upload_market_impl(h, m, true); }

@@ -144,6 +144,8 @@ void launch_block_col_sums(const double* M, int ld, const int* starts, int b0, i
 void launch_vec_scan(double* vsum, int ld, const double* M, const int* starts, int nb, int chunk, cudaStream_t st);
 void launch_tile_scan(double* store, int npairs, int n_tiles_side, const double* M, int ld, const int* starts, int nb,
                       int chunk, cudaStream_t st);
+void launch_gather_cols(const double* src, long long ld_src, double* dst, int n, long long rows, const int* cols,
+                        int sm_count, cudaStream_t st);
 void launch_gather_rows_indexed(double* M, int ld, const int* src_rows, long long dst_row0, int k0, int k1, cudaStream_t st);
 
 struct SolveParams {

@@ -523,6 +523,25 @@ void launch_gather_strided_rows(double* M, int ld, long long src_row0, int strid
     gather_strided_rows_kernel<<<k1 - k0, 128, 0, st>>>(M, ld, src_row0, stride, dst_row0, k0, k1);
 }
 
+// dst[r][j] = src[r][cols[j]]: a column subset (any order) of a row-major matrix, dense output.  HBM bound; the reads
+// of a row are scattered over its 128-byte lines, the writes are coalesced.
+__global__ void gather_cols_kernel(const double* __restrict__ src, long long ld_src, double* __restrict__ dst, int n,
+                                   long long rows, const int* __restrict__ cols) {
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const double* s = src + r * ld_src;
+        double* d = dst + r * n;
+        for (int j = threadIdx.x; j < n; j += blockDim.x) d[j] = s[cols[j]];
+    }
+}
+
+void launch_gather_cols(const double* src, long long ld_src, double* dst, int n, long long rows, const int* cols,
+                        int sm_count, cudaStream_t st) {
+    if (rows <= 0 || n <= 0) return;
+    const long long want = (long long)sm_count * 16;
+    const int grid = (int)(rows < want ? rows : want);
+    gather_cols_kernel<<<grid, n >= 256 ? 256 : 128, 0, st>>>(src, ld_src, dst, n, rows, cols);
+}
+
 // dst row (dst_row0 + k) = src row src_rows[k], k in [k0, k1): the overnight returns of arbitrary day blocks
 __global__ void gather_rows_indexed_kernel(double* __restrict__ M, int ld, const int* __restrict__ src_rows,
                                            long long dst_row0, int k0, int k1) {

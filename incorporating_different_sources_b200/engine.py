@@ -251,6 +251,63 @@ class BayesEngine:
         self.n_assets, self.n_days, self.n_hf_rows = N, D, int(desc.n_hf_rows)
         self._inflight = keep if async_copy else None
 
+    def upload_pool(self, prices, rf_row, caps=None, hf_prices=None):
+        """The FULL market (every candidate column, every row) into a resident pool; :meth:`select_market` then builds
+        the working market of a batch on the device.  ``upload_pool(None, None)`` releases the pool."""
+        if prices is None:
+            rc = self._lib.bp_upload_pool(self._h, None)
+            if rc:
+                _raise(rc)
+            self.pool_shape = None
+            return
+        prices = _c64(prices)
+        rf_row = _c64(rf_row)
+        D, N = prices.shape
+        if rf_row.shape != (D,):
+            raise ValueError("rf_row must have one entry per daily row")
+        if np.isnan(rf_row).any():
+            raise ValueError("risk-free rate undefined on some window dates (the reference would drop rows, :60)")
+        desc = MarketDesc()
+        desc.n_assets, desc.n_days = N, D
+        desc.prices, desc.rf_row = prices.ctypes.data, rf_row.ctypes.data
+        desc.caps = desc.hf_prices = desc.mcm = None
+        desc.n_hf_rows = desc.n_mcm = 0
+        keep = [prices, rf_row]
+        if caps is not None:
+            caps = _c64(caps)
+            if caps.shape != (D, N):
+                raise ValueError("caps must match prices")
+            keep.append(caps)
+            desc.caps = caps.ctypes.data
+        if hf_prices is not None and len(hf_prices):
+            hf_prices = _c64(hf_prices)
+            if hf_prices.shape[1] != N:
+                raise ValueError("hf_prices must have N columns")
+            keep.append(hf_prices)
+            desc.hf_prices = hf_prices.ctypes.data
+            desc.n_hf_rows = hf_prices.shape[0]
+        rc = self._lib.bp_upload_pool(self._h, C.byref(desc))
+        del keep
+        if rc:
+            _raise(rc)
+        self.pool_shape = (D, N, int(desc.n_hf_rows))
+
+    def select_market(self, cols, day_lo: int = 0, day_hi: Optional[int] = None, hf_lo: int = 0, hf_hi: Optional[int] = None):
+        """Working market = pool columns ``cols`` (in that order), daily rows [day_lo, day_hi), intraday rows
+        [hf_lo, hf_hi): gathered on the device.  Window rows of a following batch are relative to the slice
+        (``plan_daily_windows(..., row_offset=day_lo, hf_row_offset=hf_lo)``)."""
+        D, _, R = self.pool_shape
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        sel = _lib.PoolSelect()
+        sel.n_cols = int(cols.shape[0])
+        sel.cols = cols.ctypes.data
+        sel.day_lo, sel.day_hi = int(day_lo), int(D if day_hi is None else day_hi)
+        sel.hf_lo, sel.hf_hi = int(hf_lo), int(R if hf_hi is None else hf_hi)
+        rc = self._lib.bp_select_market(self._h, C.byref(sel))
+        if rc:
+            _raise(rc)
+        self.n_assets, self.n_days, self.n_hf_rows = int(cols.shape[0]), sel.day_hi - sel.day_lo, int(sel.hf_hi - sel.hf_lo)
+
     def set_resampled(self, rows):
         """Build the weekly return rows (:class:`~.windows.ResampledRows`) on the device from the resident prices."""
         num = np.ascontiguousarray(rows.num_row, dtype=np.int32)

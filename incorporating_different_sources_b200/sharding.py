@@ -191,12 +191,31 @@ class ShardedBacktest:
         return res
 
     def gather(self, rows, dist, group=None):
-        """All-gather per-date rows of every rank in date order.  Rank 0 has one return / turnover row fewer than
-        rebalance dates (the backtest's first date has no return, :1132): counts are adjusted per tensor."""
-        out = []
-        for x in rows:
-            cnt = list(self.counts)
-            if x.shape[0] == self.hi - self.lo - (1 if self.rank == 0 else 0) and x.dim() == 1:
-                cnt[0] -= 1
-            out.append(gather_rows(x, cnt, dist, group))
-        return out
+        """All-gather per-date rows of every rank in date order with ONE collective: the rows of a rank (weights of both
+        priors [W_local][N], returns and turnover [W_local] or, on the first rank, one row fewer -- the backtest's first
+        date has no return, :1132) are packed side by side into one [W_max][columns] buffer, gathered, and unpacked."""
+        import torch
+        if dist is None:
+            import torch.distributed as dist
+        world = dist.get_world_size(group)
+        wmax = max(self.counts)
+        own = self.hi - self.lo
+        widths = [1 if x.dim() == 1 else int(x.shape[1]) for x in rows]
+        short = [x.dim() == 1 and x.shape[0] == own - (1 if self.rank == 0 else 0) for x in rows]   # return-like rows
+        ref = rows[0]
+        pack = torch.zeros((wmax, sum(widths)), dtype=ref.dtype, device=ref.device)
+        c0 = 0
+        for x, wd, sh in zip(rows, widths, short):
+            first = 1 if (sh and self.rank == 0) else 0              # the first rank's rows start at its second date
+            view = x if x.dim() == 2 else x[:, None]
+            pack[first:first + x.shape[0], c0:c0 + wd] = view
+            c0 += wd
+        out = torch.empty((world, wmax, sum(widths)), dtype=ref.dtype, device=ref.device)
+        dist.all_gather_into_tensor(out.view(-1), pack.view(-1), group=group)
+        res, c0 = [], 0
+        for x, wd, sh in zip(rows, widths, short):
+            parts = [out[r, (1 if (sh and r == 0) else 0):self.counts[r], c0:c0 + wd] for r in range(world)]
+            full = torch.cat(parts, dim=0)
+            res.append(full if x.dim() == 2 else full[:, 0].contiguous())
+            c0 += wd
+        return res

@@ -41,7 +41,29 @@ CASES = [
     dict(name="bt_vw_daily_top5of9", market=dict(n_assets=9, n_days=60, seed=3004),
          spec=spec(weighting_strategy="vw", size=5, risk_aversion=None, mcm_scaling=None, rolling_window=20,
                    display_name="VW"), start=-15, end=-1),
+    # late listing: the stock with the largest cap has NaN prices until row 60 -> not eligible (NaN inside the 30-day
+    # window) until row 89, then it enters the top 5: NaN prices in a NON-HELD column during the first dates, a universe
+    # that changes inside the backtest
+    dict(name="bt_jeffreys_daily_top5of8_late_listing", market=dict(n_assets=8, n_days=100, seed=3007),
+         spec=spec(weighting_strategy="jeffreys", size=5, rolling_window=30, mcm_scaling=None, display_name="Jeffreys"),
+         start=-25, end=-1, damage=dict(kind="late_listing_of_largest_cap", until_row=60)),
 ]
+
+
+def apply_damage(md, damage):
+    """The same edit on the reference's and on the repo's market_data (tests/test_gpu_backtest.py imports this)."""
+    if not damage:
+        return md
+    if damage["kind"] == "late_listing_of_largest_cap":
+        caps = md["stock_market_caps_df"]
+        col = caps.columns[int(np.argmax(caps.iloc[-1].to_numpy()))]
+        md = dict(md)
+        for key in ("stock_prices_df", "stock_simple_returns_df", "stock_log_returns_df"):
+            df = md[key].copy()
+            df.iloc[:damage["until_row"], df.columns.get_loc(col)] = np.nan
+            md[key] = df
+        return md
+    raise KeyError(damage["kind"])
 
 
 def main():
@@ -52,13 +74,13 @@ def main():
             continue
         mkt = generate_market(**case["market"])
         set_universe(mkt.tickers)
-        md = mkt.market_data()
+        md = apply_damage(mkt.market_data(), case.get("damage"))
         d0, d1 = pd.Timestamp(mkt.dates[mkt.n_days + case["start"]]), pd.Timestamp(mkt.dates[mkt.n_days + case["end"]])
         res = pc.backtest_portfolio(case["spec"], d0, d1, md)
         r, t, m = (res["portfolio_simple_returns_series"], res["portfolio_turnover_series"],
                    res["portfolio_weights_metrics_df"])
         meta = dict(name=case["name"], market=case["market"], spec=case["spec"], start=str(d0.date()), end=str(d1.date()),
-                    metrics_columns=list(m.columns), series_name=r.name)
+                    metrics_columns=list(m.columns), series_name=r.name, damage=case.get("damage"))
         np.savez_compressed(os.path.join(OUT, case["name"] + ".npz"), meta=np.array(json.dumps(meta)),
                             returns=r.to_numpy(), returns_idx=r.index.values.astype("int64"),
                             turnover=t.to_numpy(), turnover_idx=t.index.values.astype("int64"),

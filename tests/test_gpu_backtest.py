@@ -34,6 +34,9 @@ def test_backtest_matches_reference(name):
     meta = json.loads(str(z["meta"]))
     mkt = generate_market(**meta["market"])
     md = mkt.market_data()
+    if meta.get("damage"):
+        from tests.golden.make_backtest_golden import apply_damage
+        md = apply_damage(md, meta["damage"])
     res = pc.backtest_portfolio(meta["spec"], pd.Timestamp(meta["start"]), pd.Timestamp(meta["end"]), md)
     r, t, m = (res["portfolio_simple_returns_series"], res["portfolio_turnover_series"],
                res["portfolio_weights_metrics_df"])

@@ -51,6 +51,46 @@ def test_universe_selection_matches_reference(freq, size):
         bt.UNIVERSE_PROVIDER = None
 
 
+@pytest.mark.parametrize("freq", ["daily", "weekly", "monthly"])
+@pytest.mark.parametrize("size", [3, 7, 50])
+def test_vectorised_universe_selection_matches_reference_on_every_date(freq, size):
+    """select_universes (all dates at once: cumulative not-NaN counts, per-day intraday counts, stable argsort) against
+    the reference's per-date get_k_largest_stocks_market_caps: membership AND order, every date of the damaged market."""
+    pc = load_reference(check=True)
+    mkt, prices, caps, intr = _damaged_market()
+    universe = list(mkt.tickers[:11]) + ["ZZZ_UNKNOWN"]
+    set_universe(universe)
+    bt.UNIVERSE_PROVIDER = lambda d: universe
+    try:
+        dates = prices.index[35:]
+        for window_days in (5, 30):
+            got, nan_bars, cand = bt.select_universes(caps, prices, intr, dates, size, window_days, freq)
+            assert len(got) == len(dates)
+            for d, names in zip(dates, got):
+                ref = pc.get_k_largest_stocks_market_caps(caps, prices, intr, d, size, window_days, freq)
+                assert names == list(ref.index), (freq, size, d, window_days)
+            # the feed of ticker 4 stops at day 80: NaN bars inside the look-back from then on, none before
+            j = cand.index(mkt.tickers[4])
+            assert nan_bars[-1, j] and not nan_bars[0, j]
+    finally:
+        bt.UNIVERSE_PROVIDER = None
+
+
+def test_vectorised_universe_selection_without_provider_and_missing_cap_date():
+    pc = load_reference(check=True)
+    mkt, prices, caps, intr = _damaged_market()
+    set_universe(mkt.tickers)
+    dates = prices.index[40:]
+    got, _, _ = bt.select_universes(caps, prices, intr, dates, 6, 20, "daily")
+    for d, names in zip(dates, got):
+        ref = pc.get_k_largest_stocks_market_caps(caps, prices, intr, d, 6, 20, "daily")
+        assert names == list(ref.index)
+    with pytest.raises(ValueError):
+        bt.select_universes(caps.drop(index=dates[3]), prices, intr, dates, 6, 20, "daily")
+    with pytest.raises(RuntimeError):
+        bt.select_universes(caps, prices, intr, dates, 6, 20, "hourly")
+
+
 def test_universe_selection_errors_match_reference():
     pc = load_reference(check=True)
     mkt, prices, caps, intr = _damaged_market()
