@@ -275,6 +275,19 @@ typedef struct {
 } bp_backtest_desc;
 int bp_backtest_batched(bp_handle* h, const bp_backtest_desc* d);
 
+/* performance_metrics (portfolio_evaluation.py:464-701) for an ENSEMBLE of return series at once (64 synthetic paths x
+ * strategies): one row of BP_PM_COUNT statistics per series.  returns / excess: [n_paths][n_obs] HOST arrays (simple
+ * returns after adjust_returns, :46-72, and excess returns, :703-719); years = (index[-1] - index[0]).days / 365 (:524);
+ * out: [n_paths][BP_PM_COUNT] host.  The probabilistic Sharpe ratio (:78-120) follows on the host from BP_PM_SKEW,
+ * BP_PM_KURT and BP_PM_SHARPE_1 of the series and of the benchmark. */
+enum {
+    BP_PM_CUM_RETURN = 0, BP_PM_CAGR, BP_PM_SHARPE, BP_PM_SORTINO, BP_PM_MAX_DD, BP_PM_CALMAR, BP_PM_AVG_LOSS,
+    BP_PM_AVG_RETURN, BP_PM_AVG_WIN, BP_PM_BEST, BP_PM_WORST, BP_PM_ANN_VOL, BP_PM_DAILY_VAR, BP_PM_SKEW, BP_PM_KURT,
+    BP_PM_SHARPE_1, BP_PM_COUNT
+};
+int bp_path_metrics(bp_handle* h, int n_paths, int n_obs, const double* returns, const double* excess, double years,
+                    double* out);
+
 /* calculate_excess_log_returns_from_prices (:31-62) of ONE window (b->n_windows == 1):
  * X is [(rolling_window-1)][N]. */
 int bp_excess_returns(bp_handle* h, const bp_window_batch* b, double* X);

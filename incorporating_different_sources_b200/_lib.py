@@ -28,7 +28,7 @@ EXPORTED = [
     "bp_excess_returns", "bp_quadratic_form", "bp_dense_posterior", "bp_moments_batched",
     "bp_upload_market_async", "bp_backtest_batched", "bp_get_gram_work", "bp_set_reuse_min_windows", "bp_set_upload_pipeline", "bp_set_async_outputs",
     "bp_set_resampled", "bp_estimator_batched", "bp_set_jeffreys_chain", "bp_get_solve_work",
-    "bp_set_upload_fractions", "bp_solve_wave_windows", "bp_set_hf_presum_min_days", "bp_wait_upload", "bp_upload_pool", "bp_select_market",
+    "bp_set_upload_fractions", "bp_solve_wave_windows", "bp_set_hf_presum_min_days", "bp_wait_upload", "bp_upload_pool", "bp_select_market", "bp_path_metrics",
 ]
 BP_NSTAGE = 8
 STAGES = ("logret", "prep", "gram", "solve", "chain")
@@ -117,6 +117,7 @@ def load():
     lib.bp_wait_upload.argtypes = [C.c_void_p]
     lib.bp_upload_pool.argtypes = [C.c_void_p, C.POINTER(MarketDesc)]
     lib.bp_select_market.argtypes = [C.c_void_p, C.POINTER(PoolSelect)]
+    lib.bp_path_metrics.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, C.c_double, c_double_p]
     lib.bp_set_workspace_limit.argtypes = [C.c_void_p, C.c_size_t]
     lib.bp_device_info.argtypes = [C.c_void_p, c_int_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.bp_launch_count.argtypes = [C.c_void_p]

@@ -1729,6 +1729,29 @@ static int upload_market_impl(bp_handle* h, const bp_market_desc* m, bool blocki
     return BP_OK;
 }
 
+int bp_path_metrics(bp_handle* h, int n_paths, int n_obs, const double* returns, const double* excess, double years,
+                    double* out) {
+    if (!h || !returns || !excess || !out) return fail(BP_ERR_INVALID, "null handle or array");
+    if (n_paths <= 0 || n_obs < 2) return fail(BP_ERR_INVALID, "need at least one series of two returns");
+    if (!(years > 0.0)) return fail(BP_ERR_INVALID, "years must be positive");
+    CU_TRY(cudaSetDevice(h->device));
+    const size_t n = (size_t)n_paths * n_obs;
+    int rc = ensure_stage(h, sizeof(double) * (2 * n + (size_t)n_paths * BP_PM_COUNT));
+    if (rc) return rc;
+    double* d = reinterpret_cast<double*>(h->stage);
+    cudaStream_t st = h->stream;
+    CU_TRY(cudaMemcpyAsync(d, returns, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d + n, excess, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    PathMetricsParams p{};
+    p.n_paths = n_paths; p.n_obs = n_obs; p.ld = n_obs;
+    p.returns = d; p.excess = d + n; p.years = years; p.out = d + 2 * n;
+    CU_TRY(launch_path_metrics(p, st));
+    h->launches++;
+    CU_TRY(cudaMemcpyAsync(out, d + 2 * n, sizeof(double) * (size_t)n_paths * BP_PM_COUNT, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return BP_OK;
+}
+
 int bp_upload_pool(bp_handle* h, const bp_market_desc* m) {
     if (!h) return fail(BP_ERR_INVALID, "null handle");
     CU_TRY(cudaSetDevice(h->device));

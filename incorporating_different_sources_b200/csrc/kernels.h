@@ -204,6 +204,17 @@ struct LoopParams {
 };
 cudaError_t launch_backtest_loop(const LoopParams& p, cudaStream_t st);
 
+// evaluation statistics of a path ensemble (eval_kernels.cu); the BP_PM_* indices are declared in bayes_portfolio.h
+struct PathMetricsParams {
+    int n_paths, n_obs;
+    long long ld;                // row stride of returns / excess
+    const double* returns;       // [P][ld] simple returns
+    const double* excess;        // [P][ld] excess simple returns (compute_excess_returns, :703-719)
+    double years;                // (index[-1] - index[0]).days / 365  (CAGR, :520-524)
+    double* out;                 // [P][BP_PM_COUNT]
+};
+cudaError_t launch_path_metrics(const PathMetricsParams& p, cudaStream_t st);
+
 void launch_gather_log_returns(const double* P, int ld_in, const int* num, const int* den, double* out, int ld_out,
                                int rows, int n_assets, cudaStream_t st);
 void launch_range_sum(const double* store, const int* ranges, int n_ranges, int npairs, double* out, cudaStream_t st);
