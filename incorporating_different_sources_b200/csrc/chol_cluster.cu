@@ -511,8 +511,9 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 int chol_cluster_size(int n_windows, int cta_slots) {
     static const int forced = env_int("BP_CHOL_CLUSTER", -1, 0, CC_MAX_CLUSTER);
     if (forced >= 0) return forced;
+    static const int slack_pct = env_int("BP_CHOL_CLUSTER_SLACK_PCT", 100, 100, 400);
     int k = CC_MAX_CLUSTER;
-    while (k > 1 && (long long)n_windows * k > cta_slots) k >>= 1;
+    while (k > 1 && (long long)n_windows * k * 100 > (long long)cta_slots * slack_pct) k >>= 1;
     return k > 1 ? k : 0;
 }
 

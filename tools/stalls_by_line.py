@@ -10,8 +10,11 @@ def main(path, top=40):
     hdr = rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
     reasons = [h for h in hdr if h.startswith("stall_") and "(" not in h]
-    agg, tot = [], 0.0
+    agg, tot, seen = [], 0.0, set()
     for r in rows[2:]:
+        if r and r[0] in seen:          # a report section repeated (two metric sections of one launch)
+            continue
+        seen.add(r[0] if r else None)
         try:
             v = float(r[ix["# Samples"]])
         except Exception:
@@ -21,7 +24,11 @@ def main(path, top=40):
         agg.append((v, r[ix["Source"]].strip()[:100], ", ".join(f"{k} {int(x)}" for x, k in rs if x > 0)))
     agg.sort(reverse=True)
     print(f"total samples {tot:.0f}")
-    by_reason = {k: sum(float(r[ix[k]] or 0) for r in rows[2:] if len(r) > ix[k] and r[ix[k]].replace('.', '').isdigit()) for k in reasons}
+    uniq = {}
+    for r in rows[2:]:
+        if r and r[0] not in uniq:
+            uniq[r[0]] = r
+    by_reason = {k: sum(float(r[ix[k]] or 0) for r in uniq.values() if len(r) > ix[k] and r[ix[k]].replace('.', '').isdigit()) for k in reasons}
     print("by reason:", ", ".join(f"{k[6:]} {100 * v / tot:.1f}%" for k, v in sorted(by_reason.items(), key=lambda kv: -kv[1]) if v > 0.005 * tot))
     for v, s, why in agg[:top]:
         print(f"{100 * v / tot:5.1f}%  {s:100s}  [{why}]")
