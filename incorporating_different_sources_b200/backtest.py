@@ -59,14 +59,15 @@ def get_k_largest_stocks_market_caps(stock_market_caps_df, stock_prices_df, stoc
 
 
 def select_universes(stock_market_caps_df, stock_prices_df, stock_intraday_prices_df, trade_dates, portfolio_size,
-                     rolling_window_days, rolling_window_frequency):
+                     rolling_window_days, rolling_window_frequency, lookback_days=None):
     """``get_k_largest_stocks_market_caps`` (:611-658) for ALL trade dates at once: rolling not-NaN counts of the
     daily prices (cumulative sums), per-calendar-day not-NaN counts of the intraday bars, and a stable descending
     argsort of the caps row (= ``nlargest``'s first-occurrence tie rule, F7).  Returns one ordered ticker list per
     date — membership AND order identical to the per-date function (tests/test_host_vs_reference.py).
 
     Also returns ``nan_bars`` [T][C] (bool, in candidate order) = the stock has a NaN bar inside the date's intraday
-    LOOK-BACK, and the candidate list: the reference would drop such bars (``dropna``, :314); the batched path raises."""
+    LOOK-BACK of ``lookback_days`` calendar days (default: the eligibility range's own length), and the candidate list:
+    the reference would drop such bars (``dropna``, :314); the batched path raises."""
     if rolling_window_frequency not in HF_LOOKBACK_DAYS:
         raise RuntimeError("Unknown rolling window frequency.")                                   # :637
     days = HF_LOOKBACK_DAYS[rolling_window_frequency]
@@ -116,7 +117,8 @@ def select_universes(stock_market_caps_df, stock_prices_df, stock_intraday_price
     a = np.searchsorted(bucket_day, d_day - np.timedelta64(days, "D"), side="left")
     b = np.searchsorted(bucket_day, d_day, side="right")
     ok_intr = (cnt[b] - cnt[a]) > 0
-    a_look = np.searchsorted(bucket_day, d_day - np.timedelta64(days, "D") + np.timedelta64(1, "D"), side="left")
+    look = days if lookback_days is None else int(lookback_days)
+    a_look = np.searchsorted(bucket_day, d_day - np.timedelta64(look, "D") + np.timedelta64(1, "D"), side="left")
     nan_bars = (nanc[b] - nanc[a_look]) > 0
     # caps row of each date: eligible, not NaN, k largest in first-occurrence order (:649-653)
     rows = stock_market_caps_df.index.get_indexer(trade_dates)
@@ -344,8 +346,10 @@ def backtest_portfolio(portfolio_spec, ts_start_date, ts_end_date, market_data, 
     universes, nan_bars, cand = select_universes(market_data["stock_market_caps_df"], prices_df,
                                                  market_data["stock_intraday_prices_df"], dates_all[reb_pos],
                                                  portfolio_spec["size"], get_window_trading_days(portfolio_spec),
-                                                 portfolio_spec["rebalancing_frequency"])      # sic (:960)
-    if nan_bars is not None and portfolio_spec["weighting_strategy"].startswith("conjugate") and hf_lookback_days is None:
+                                                 portfolio_spec["rebalancing_frequency"],      # sic (:960)
+                                                 lookback_days=hf_lookback_days if hf_lookback_days is not None else
+                                                 HF_LOOKBACK_DAYS.get(portfolio_spec["rolling_window_frequency"]))
+    if nan_bars is not None and portfolio_spec["weighting_strategy"].startswith("conjugate"):
         pos_of = {s: j for j, s in enumerate(cand)}
         for r, names in enumerate(universes):
             hit = [s for s in names if nan_bars[r, pos_of[s]]]
