@@ -413,19 +413,23 @@ def run_ours(args):
              "status": torch.empty((W,), dtype=torch.int32, device=dev)}
     out_j = {"weights": torch.empty((W, N), dtype=torch.float64, device=dev),
              "status": torch.empty((W,), dtype=torch.int32, device=dev)}
-    gathered = None
+    gathered_c = gathered_j = None
     if world > 1:
-        gathered = torch.empty((world, 2, W, N), dtype=torch.float64, device=dev)
-        mine = torch.empty((2, W, N), dtype=torch.float64, device=dev)
+        gathered_c = torch.empty((world, W, N), dtype=torch.float64, device=dev)
+        gathered_j = torch.empty((world, W, N), dtype=torch.float64, device=dev)
 
     def step_device():
         eng.prepare_market()
         eng.conjugate(cb, outputs=("weights", "status"), into=out_c)
+        if world > 1:
+            # the gather of the conjugate weights travels over NVLink while the Jeffreys windows are computed
+            # (NCCL's stream waits for the kernels queued so far; the compute stream goes on)
+            hc = dist.all_gather_into_tensor(gathered_c.view(-1), out_c["weights"].view(-1), async_op=True)
         eng.jeffreys(jb, outputs=("weights", "status"), into=out_j)
         if world > 1:
-            mine[0].copy_(out_c["weights"])
-            mine[1].copy_(out_j["weights"])
-            dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))
+            hj = dist.all_gather_into_tensor(gathered_j.view(-1), out_j["weights"].view(-1), async_op=True)
+            hc.wait()
+            hj.wait()
 
     hw_c, hw_cv = pin(np.zeros((W, N)))
     hw_j, hw_jv = pin(np.zeros((W, N)))
@@ -489,7 +493,7 @@ def run_ours(args):
     gwork = eng.gram_work()
     swork = eng.solve_work()
     eng.set_stage_timing(False)
-    launches = (eng.launch_count - launches0) // args.steps + (3 if world > 1 else 0)
+    launches = (eng.launch_count - launches0) // args.steps + (2 if world > 1 else 0)      # + the two all-gathers
     status_bad = int((out_c["status"] != 0).sum().item() + (out_j["status"] != 0).sum().item())
     value = n_gpus * 2 * W / (ms * 1e-3)
 

@@ -294,6 +294,8 @@ def run_c5(args):
                           mcm=ctx.pin(np.stack([mkt.vix, mkt.epu])), rf_row=ctx.pin(ffill_rows(mkt.dates, mkt.dates, mkt.rf))))
         batches.append((cb, jb))
         n_hf = hi - lo
+        if k == 0 and ctx.rank == 0:
+            parity_ref = (mkt, conj, jeff)           # the first market of rank 0 is re-checked against the oracle below
         del mkt
     W = len(d_idx)
     h2d_path = int(sum(v.nbytes for v in hosts[0].values()))
@@ -354,6 +356,18 @@ def run_c5(args):
     torch.cuda.synchronize()
     launches = sum(e.launch_count for e in engs) - launches0 + per_gpu * (3 if ctx.world > 1 else 2)
     bad = ctx.sum_over_ranks(float(sum((o["status"] != 0).sum().item() for pair in outs for o in pair)))
+    parity = None
+    if ctx.rank == 0 and not args.no_cpu:
+        # engine 0 holds rank 0's first market: a few of its windows against the CPU oracle (1e-9 bar)
+        from oracle import bayes_oracle as bo
+        mkt0, conj0, jeff0 = parity_ref
+        cols = np.arange(N)
+        wc, wj = outs[0][0]["weights"].cpu().numpy(), outs[0][1]["weights"].cpu().numpy()
+        parity = 0.0
+        for i in np.linspace(0, W - 1, 4).round().astype(int):
+            for got, ref in ((wc[i], bo.conjugate_window(conj0, mkt0, int(d_idx[i]), cols, hf_lookback_days=args.hf_days)["weights"]),
+                             (wj[i], bo.jeffreys_window(jeff0, mkt0, int(d_idx[i]), cols)["weights"])):
+                parity = max(parity, float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))))
     e2e_steps = max(1, min(args.steps, 2))
     e2e_s = ctx.time_wall(step_e2e, e2e_steps)
     ceiling = ctx.h2d_ceiling(h2d_path)
@@ -386,7 +400,7 @@ def run_c5(args):
                          "traffic": None, "solve_conventional_tflops": solve_tf,
                          "note": "conventional flops per GPU (SURVEY 8(d)); > 1 reflects block reuse and the Jeffreys chain, "
                                  "see the C2 line for the per-kernel rooflines"},
-            "windows_flagged_singular": int(bad),
+            "windows_flagged_singular": int(bad), "parity_max_rel_err": parity,
         }
         print(json.dumps(line), flush=True)
     for e in engs:
