@@ -63,3 +63,48 @@ def test_date_range_shards_equal_unsharded_backtest(engine, world):
         assert relerr(got[0][i], ref["weights"]) <= 1e-9
         ref = bo.jeffreys_window(jeff, mkt, int(d_idx[i]), cols)
         assert relerr(got[1][i], ref["weights"]) <= 1e-9
+
+
+def test_pool_gather_equals_direct_upload(engine):
+    """bp_upload_pool + bp_select_market (device gather of a column subset in a given order and of a row range) must
+    leave exactly the working market a direct upload of the same slice leaves: bit-identical weights; and the error
+    paths of the two entry points."""
+    from incorporating_different_sources_b200.engine import BayesPortfolioError
+    from incorporating_different_sources_b200.synthetic import generate_market
+    from incorporating_different_sources_b200.windows import ffill_rows, plan_daily_windows
+    N_all, n, W = 30, 50, 40
+    mkt = generate_market(N_all, n + W + 20, seed=8)
+    spec = dict(weighting_strategy="conjugate_hf_epu_vw", size=12, risk_aversion=4, rolling_window=n,
+                rolling_window_frequency="daily", mcm_scaling=1)
+    cols = np.random.default_rng(1).permutation(N_all)[:12]
+    d_idx = np.arange(n + 10, n + 10 + W)
+    day_lo, day_hi = int(d_idx.min()) - (n - 1), int(d_idx.max()) + 1
+    day = np.timedelta64(1, "D")
+    hf_lo = int(np.searchsorted(mkt.hf_ts, mkt.dates[d_idx.min()] - 7 * day + day, side="right")) - 1
+    hf_hi = int(np.searchsorted(mkt.hf_ts, mkt.dates[d_idx.max()] + day, side="right"))
+    rf_row = ffill_rows(mkt.dates, mkt.dates, mkt.rf)
+    batch = plan_daily_windows(spec, mkt.dates, d_idx, mkt.hf_ts, hf_lookback_days=7, row_offset=day_lo, hf_row_offset=hf_lo)
+    batch.prior_n = np.full(W, 61.5)                     # no MCM series in the pool: n0 is injected (as backtest.py does)
+    outs = ("weights", "w1", "scalars", "status")
+    engine.upload_market(prices=mkt.prices[day_lo:day_hi][:, cols], rf_row=rf_row[day_lo:day_hi],
+                         caps=mkt.caps[day_lo:day_hi][:, cols], hf_prices=mkt.hf_prices[hf_lo:hf_hi][:, cols])
+    ref = engine.conjugate(batch, outputs=outs)
+    with pytest.raises(BayesPortfolioError):
+        engine.pool_shape = (mkt.n_days, N_all, len(mkt.hf_ts))
+        engine.select_market(cols, day_lo, day_hi, hf_lo, hf_hi)          # no pool resident yet
+    engine.upload_pool(prices=mkt.prices, rf_row=rf_row, caps=mkt.caps, hf_prices=mkt.hf_prices)
+    engine.select_market(cols, day_lo, day_hi, hf_lo, hf_hi)
+    got = engine.conjugate(batch, outputs=outs)
+    assert not ref["status"].any()
+    for k in outs:
+        assert np.array_equal(got[k], ref[k]), k
+    # a second selection from the same pool (other columns, other rows) and back: still identical
+    engine.select_market(np.arange(5), 0, 60, 0, 200)
+    engine.select_market(cols, day_lo, day_hi, hf_lo, hf_hi)
+    assert np.array_equal(engine.conjugate(batch, outputs=("weights",))["weights"], ref["weights"])
+    for bad in (dict(cols=[N_all]), dict(day_lo=-1), dict(day_hi=mkt.n_days + 1), dict(hf_hi=len(mkt.hf_ts) + 1), dict(cols=[])):
+        kw = dict(cols=cols, day_lo=day_lo, day_hi=day_hi, hf_lo=hf_lo, hf_hi=hf_hi)
+        kw.update(bad)
+        with pytest.raises(ValueError):                    # BP_ERR_INVALID maps to ValueError (engine._raise)
+            engine.select_market(**kw)
+    engine.upload_pool(None, None)
