@@ -1194,9 +1194,12 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
             // occupancy whichever of the copy and the GPU is the bottleneck.
             if (!last) {
                 const int wave = chol_wave_windows(h->sm_count);
-                // (solving partial waves between short tail segments was measured and dropped: a launch costs the
-                // latency of one factorisation, 1.1 ms, however few windows it has)
-                const int wn = (w_done - w_solved) / wave * wave;
+                // Full waves only -- a launch costs the latency of one factorisation however few windows it has -- except
+                // before the LAST segment: whatever is ready then is solved while the last segment is on the bus, so that
+                // only the last segment's own windows follow the copy (with the default plan that is a full wave anyway;
+                // plans with several short tail segments were measured slower, windows.plan_wave_fractions)
+                const bool before_last = s == h->n_seg - 2;
+                const int wn = before_last ? w_done - w_solved : (w_done - w_solved) / wave * wave;
                 if (wn > 0) {
                     if ((rc = solve_range(w_solved, wn))) return rc;
                     w_solved += wn;

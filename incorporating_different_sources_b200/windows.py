@@ -114,23 +114,28 @@ def plan_daily_windows(spec, dates: np.ndarray, d_indices: Sequence[int], hf_ts:
     )
 
 
-def plan_wave_fractions(hf_hi: np.ndarray, n_hf_rows: int, wave: int, max_segments: int = 8):
+def plan_wave_fractions(hf_hi: np.ndarray, n_hf_rows: int, wave: int, max_segments: int = 8, tail_split: int = 1):
     """Cut points of a segmented intraday upload for a date-sorted conjugate batch (``bp_set_upload_fractions``):
-    whole solver waves of windows per segment (several per segment when there are more waves than segments), the
-    remainder as the last one.  A solver launch costs the latency of one factorisation however few windows it has, so
-    short tail segments only add launches (measured: halving the remainder made the step 6 ms slower).  Returns the
-    cumulative row fractions, or ``None`` when the batch is too small or not sorted by date."""
+    whole solver waves of windows per segment (several per segment when there are more waves than segments), then the
+    remainder of the batch as ``tail_split`` segments.  Between segments the library solves full waves only (a solver
+    launch costs the latency of one factorisation however few windows it has); before the LAST segment it solves
+    everything that is ready.  Cutting the remainder in two or three so that less work follows the copy was measured on
+    the C2 workload (tools/e2e_tail.py): 29.00 ms (one tail segment) / 29.55 (two) / 29.41 (three) -- the short launches
+    are too inefficient, the GPU falls behind the bus -- hence the default of 1.  Returns the cumulative row fractions,
+    or ``None`` when the batch is too small or not sorted by date."""
     hi = np.asarray(hf_hi, dtype=np.int64)
     W = int(hi.shape[0])
     if wave <= 0 or W < 2 * wave or max_segments < 2 or np.any(np.diff(hi) < 0):
         return None
     full = W // wave
-    per = -(-full // (max_segments - 1))
+    rest = W - full * wave
+    n_tail = max(1, min(int(tail_split), max_segments - 1)) if rest >= 128 * max(1, int(tail_split)) else (1 if rest > 0 else 0)
+    per = -(-full // max(1, max_segments - n_tail))
     counts = [per * wave] * (full // per)
     if full % per:
         counts.append((full % per) * wave)
-    if W - full * wave > 0:
-        counts.append(W - full * wave)
+    for k in range(n_tail):
+        counts.append(rest // n_tail + (1 if k < rest % n_tail else 0))
     ends = np.cumsum(counts)
     return [float(hi[e - 1]) / float(n_hf_rows) for e in ends]
 

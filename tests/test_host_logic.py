@@ -122,6 +122,11 @@ def test_upload_segment_planner_and_intraday_trim():
     # more waves than segments: several waves per segment, never more than max_segments
     fr = plan_wave_fractions(b.hf_hi, R, wave=10, max_segments=8)
     assert len(fr) <= 8 and fr[-1] == 1.0
+    # optional: the remainder cut into several tail segments (measured slower on the C2 workload, default 1)
+    hi = np.arange(1, 1461) * 10
+    assert [int(round(f * 14600)) // 10 for f in plan_wave_fractions(hi, 14600, wave=400)] == [400, 800, 1200, 1460]
+    fr = plan_wave_fractions(hi, 14600, wave=400, tail_split=2)
+    assert [int(round(f * 14600)) // 10 for f in fr] == [400, 800, 1200, 1330, 1460]
     assert plan_wave_fractions(b.hf_hi, R, wave=200) is None                       # less than two waves
     assert plan_wave_fractions(b.hf_hi[::-1], R, wave=60) is None                  # not sorted by date
     lo0, hi0 = b.hf_lo.copy(), b.hf_hi.copy()
