@@ -441,6 +441,13 @@ def run_ours(args):
     # segments of the pipelined upload: one solver wave of ready windows per segment, then halves
     e2e_fractions = eng.plan_upload_fractions(cb, hf_used.shape[0])
 
+    # long look-backs take the pre-summed day-block path, which is not pipelined against the upload inside one call:
+    # the conjugate batch is cut along the upload segments instead, and each sub-batch waits for its own segments only
+    from incorporating_different_sources_b200.windows import split_batch_by_fractions
+    sub_batches = None
+    if args.hf_days >= 12 and e2e_fractions:
+        sub_batches = split_batch_by_fractions(cb, e2e_fractions, hf_used.shape[0])
+
     def step_e2e():
         # pinned host buffers -> HBM (the 1.6 GB intraday block in segments on the copy stream), Jeffreys first
         # because it does not read intraday data and so overlaps the transfer, then conjugate, pipelined against
@@ -450,7 +457,11 @@ def run_ours(args):
         eng.set_upload_fractions(e2e_fractions)
         eng.upload_market(**host, async_copy=True)
         eng.jeffreys(jb, outputs=("weights", "status"), into={"weights": hw_jv, "status": hs_j})
-        eng.conjugate(cb, outputs=("weights", "status"), into={"weights": hw_cv, "status": hs_c})
+        if sub_batches:
+            for i0, i1, sb in sub_batches:
+                eng.conjugate(sb, outputs=("weights", "status"), into={"weights": hw_cv[i0:i1], "status": hs_c[i0:i1]})
+        else:
+            eng.conjugate(cb, outputs=("weights", "status"), into={"weights": hw_cv, "status": hs_c})
         eng.synchronize()
         eng.set_async_outputs(False)
         eng.set_upload_fractions(None)
@@ -507,7 +518,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     e2e_value = n_gpus * 2 * W / e2e_s
-    e2e_match = bool(np.array_equal(hw_cv, out_c["weights"].cpu().numpy()))
+    if sub_batches:      # sub-batches anchor their block grids differently: same sums, different association
+        ref_w = out_c["weights"].cpu().numpy()
+        e2e_match = bool(np.max(np.abs(hw_cv - ref_w)) <= 1e-10 * np.max(np.abs(ref_w)))
+    else:
+        e2e_match = bool(np.array_equal(hw_cv, out_c["weights"].cpu().numpy()))
     # platform limit of the e2e leg: every rank copies a buffer of its intraday block's size at once (plain cudaMemcpyAsync)
     hf_t = keep[2]
     torch.cuda.synchronize()
@@ -612,6 +627,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_s * 1e3, "matches_device_path": e2e_match, "steps": e2e_steps,
                     "inputs": "host buffers pinned once outside the timed region; windows planned once outside it",
+                    "conjugate_sub_batches": len(sub_batches) if sub_batches else 1,
                     "h2d_ceiling": h2d_ceiling,
                     "h2d_ms_at_ceiling": h2d_bytes / (h2d_ceiling["per_rank_gbs"] * 1e9) * 1e3,
                     "frac_of_h2d_ceiling": (h2d_bytes / (h2d_ceiling["per_rank_gbs"] * 1e9)) / e2e_s},

@@ -463,15 +463,22 @@ def run_c3(args):
     hw = torch.empty((W, N), dtype=torch.float64).pin_memory()
     hs = torch.empty((W,), dtype=torch.int32).pin_memory()
 
+    # (cutting the batch along upload segments, as bench.py does for C2 with long look-backs, was measured here too:
+    # 8.35 instead of 7.95 ms -- at N = 100 every sub-batch is latency bound and repeats the 252-day halo)
+    subs = [(0, W, cb)]
+    hwv, hsv = hw.numpy(), hs.numpy()
+
     def step_e2e():
         eng.set_async_outputs(True)
         eng.upload_market(**host, async_copy=True)
-        eng.conjugate(cb, outputs=("weights", "status"), into={"weights": hw.numpy(), "status": hs.numpy()})
+        eng.conjugate(cb, outputs=("weights", "status"), into={"weights": hwv, "status": hsv})
         eng.synchronize()
         eng.set_async_outputs(False)
 
     e2e_s = ctx.time_wall(step_e2e, max(1, min(args.steps, 3)))
     h2d = int(sum(v.nbytes for v in host.values()))
+    ceiling = ctx.h2d_ceiling(h2d)
+    e2e_err = float(np.max(np.abs(hwv - out["weights"].cpu().numpy())) / np.max(np.abs(hwv)))
     # parity + CPU port on a bounded sample (each oracle window contracts 19.6k x 100 intraday returns)
     cols = np.arange(N)
     sel = np.linspace(0, W - 1, max(2, args.cpu_sample // 32)).round().astype(int)
@@ -498,11 +505,12 @@ def run_c3(args):
                    "cache": "intraday block (%.2f GB) larger than L2" % ((hi - lo) * N * 8 / 1e9)},
         "clocks": clocks,
         "e2e": {"value": W / e2e_s, "unit": B.UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(hw.numel() * 8 + hs.numel() * 4),
-                "ms_per_step": e2e_s * 1e3, "inputs": "pre-pinned host buffers"},
+                "ms_per_step": e2e_s * 1e3, "inputs": "pre-pinned host buffers", "conjugate_sub_batches": len(subs),
+                "h2d_ceiling": ceiling, "h2d_ms_at_ceiling": h2d / (ceiling["per_rank_gbs"] * 1e9) * 1e3},
         "gpu_launches": int(launches), "roofline": roof, "stages_ms": st,
         "cpu_baseline": {"value": len(sel) / cpu_dt, "unit": B.UNIT, "cores": B.blas_threads(), "kind": "port",
                          "sample": f"{len(sel)} windows, oracle/bayes_oracle.py, one process, NumPy default BLAS threads"},
-        "parity_max_rel_err": worst,
+        "parity_max_rel_err": worst, "e2e_vs_device_path_max_rel_diff": e2e_err,
         "windows_flagged_singular": int((out["status"] != 0).sum().item()),
     }
     print(json.dumps(line), flush=True)

@@ -222,6 +222,29 @@ int wait_hf(bp_handle* h) {
     return BP_OK;
 }
 
+// The same for a batch that reads intraday PRICE rows < rows_needed only: waits for the upload segments that cover them
+// and computes their log returns; the later segments stay pending.  A caller that cuts a date-sorted batch into
+// sub-batches along the segment boundaries thereby overlaps the compute of sub-batch k with the copy of segment k+1 on
+// ANY path (the pipelined branch of run_batches does this inside one call, but only for the one-tile-per-day form).
+int wait_hf_rows(bp_handle* h, long long rows_needed) {
+    if (!h->hf_pending) return BP_OK;
+    if (h->n_seg <= 1 || rows_needed >= h->R) return wait_hf(h);
+    while (h->seg_waited < h->n_seg && h->lr_hf_done < rows_needed) {
+        const int s = h->seg_waited;
+        CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_seg[s], 0));
+        launch_log_returns(h->hf_prices, h->N, h->lr_hf, h->ld, h->seg_end[s], h->N, h->sm_count, h->stream, h->lr_hf_done);
+        h->launches++;
+        CU_TRY(cudaGetLastError());
+        h->lr_hf_done = h->seg_end[s];
+        h->seg_waited = s + 1;
+    }
+    if (h->seg_waited >= h->n_seg) {
+        h->hf_pending = false;
+        h->lr_hf_done = h->R;
+    }
+    return BP_OK;
+}
+
 int make_map(bp_handle* h, CUtensorMap* map, const double* base, long long rows, int ld) {
     // 3-D view (16-column group element, row, column group) of a row-major [rows][ld] matrix
     cuuint64_t dims[3] = {16, (cuuint64_t)rows, (cuuint64_t)(ld / 16)};
@@ -1063,7 +1086,11 @@ int run_batches(bp_handle* h, const bp_window_batch* b, const bp_outputs* out, i
     // arrived run while the rest is still being copied; the solve follows for all windows at once.
     const bool pipelined = mode == BP_MODE_CONJUGATE && h->hf_pending && h->n_seg > 1 && h->seg_waited < h->n_seg &&
                            solve && !out->T && !out->S0 && Wc >= B.W && !B.presum;
-    if (mode == BP_MODE_CONJUGATE && !pipelined && (rc = wait_hf(h))) return rc;
+    if (mode == BP_MODE_CONJUGATE && !pipelined) {
+        long long need = 0;                   // intraday price rows this batch reads
+        for (int w = 0; w < B.W; ++w) need = std::max<long long>(need, b->hf_hi[w]);
+        if ((rc = wait_hf_rows(h, need))) return rc;
+    }
     rc = ensure_ws(h, (size_t)Wc * L.per_window + 256);
     if (rc) return rc;
     const Chunk c = carve(h->ws, L, Wc);

@@ -140,6 +140,36 @@ def plan_wave_fractions(hf_hi: np.ndarray, n_hf_rows: int, wave: int, max_segmen
     return [float(hi[e - 1]) / float(n_hf_rows) for e in ends]
 
 
+def slice_batch(batch: WindowBatch, i0: int, i1: int) -> WindowBatch:
+    """Windows [i0, i1) of a batch (views of the per-window arrays, same scalars)."""
+    import dataclasses
+    cut = lambda a: None if a is None else a[i0:i1]
+    return dataclasses.replace(batch, day_row=batch.day_row[i0:i1], span_days=batch.span_days[i0:i1], hf_lo=cut(batch.hf_lo),
+                               hf_hi=cut(batch.hf_hi), prior_n=cut(batch.prior_n), extra_row=cut(batch.extra_row),
+                               caps_row=cut(batch.caps_row))
+
+
+def split_batch_by_fractions(batch: WindowBatch, cum_fractions: Sequence[float], n_hf_rows: int):
+    """Cut a date-sorted conjugate batch along the segment boundaries of a segmented upload
+    (``plan_wave_fractions``): sub-batch k holds the windows whose last intraday row lies in segment k.  Evaluated one
+    after the other behind an asynchronous upload, sub-batch k only waits for segments <= k (``wait_hf_rows`` in the
+    library), so its compute overlaps the copy of the later segments -- on every path, including the pre-summed day
+    blocks of long look-backs, which are not pipelined inside one call.  Returns [(i0, i1, sub_batch), ...]."""
+    hi = np.asarray(batch.hf_hi, dtype=np.int64)
+    if np.any(np.diff(hi) < 0):
+        raise ValueError("the batch must be sorted by date")
+    out, i0 = [], 0
+    for f in cum_fractions:
+        # same rounding as the library (bp_upload_market_async: ceil(f * R))
+        i1 = int(np.searchsorted(hi, int(np.ceil(f * n_hf_rows)), side="right"))
+        if i1 > i0:
+            out.append((i0, i1, slice_batch(batch, i0, i1)))
+            i0 = i1
+    if i0 < len(hi):
+        out.append((i0, len(hi), slice_batch(batch, i0, len(hi))))
+    return out
+
+
 def trim_intraday(batch: WindowBatch):
     """Row range ``[lo, hi)`` of the intraday matrix that the windows of ``batch`` read; the batch is shifted in place
     so that it refers to ``hf_prices[lo:hi]``.  Bars outside the range (e.g. the years of history before the first
