@@ -129,6 +129,15 @@ def test_upload_segment_planner_and_intraday_trim():
     assert [int(round(f * 14600)) // 10 for f in fr] == [400, 800, 1200, 1330, 1460]
     assert plan_wave_fractions(b.hf_hi, R, wave=200) is None                       # less than two waves
     assert plan_wave_fractions(b.hf_hi[::-1], R, wave=60) is None                  # not sorted by date
+    # sub-batches along the segment boundaries: a partition of the windows in date order; the windows of sub-batch k
+    # end inside segment k (so that it only waits for segments <= k)
+    from incorporating_different_sources_b200.windows import split_batch_by_fractions
+    fr = plan_wave_fractions(b.hf_hi, R, wave=60)
+    subs = split_batch_by_fractions(b, fr, R)
+    assert [i1 - i0 for i0, i1, _ in subs] == [60, 60, 60, 60, 10] and subs[0][0] == 0 and subs[-1][1] == 250
+    for (i0, i1, sb), f in zip(subs, fr):
+        assert sb.n_windows == i1 - i0 and np.array_equal(sb.hf_hi, b.hf_hi[i0:i1]) and np.array_equal(sb.day_row, b.day_row[i0:i1])
+        assert sb.hf_hi.max() <= int(np.ceil(f * R)) and sb.rolling_window == b.rolling_window
     lo0, hi0 = b.hf_lo.copy(), b.hf_hi.copy()
     lo, hi = trim_intraday(b)
     assert lo == lo0.min() > 0 and hi == hi0.max() == R
