@@ -248,6 +248,26 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
                     const unsigned char* sA = stage_mem + stage * CH_STAGE_BYTES;
                     const unsigned char* sB = sA + ABOXES * BOX_BYTES;
                     mbar_wait(&full_bar[stage], (it / CH_STAGES) & 1);
+                    if (ni == TPW) {
+                        // full slab (all but the last slab of a panel): no per-tile predicate, so the loads of a k-step
+                        // are issued together and its TPW x 4 DMMAs follow without branches or re-convergence points
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            double b[4], a[TPW];
+#pragma unroll
+                            for (int nt = 0; nt < 4; ++nt)
+                                b[nt] = *reinterpret_cast<const double*>(sB + nt * 1024 + foff[q]);
+#pragma unroll
+                            for (int i = 0; i < TPW; ++i) {
+                                const int t = warp + CH_WARPS * i;
+                                a[i] = *reinterpret_cast<const double*>(sA + (t >> 2) * BOX_BYTES + (t & 3) * 1024 + foff[q]);
+                            }
+#pragma unroll
+                            for (int i = 0; i < TPW; ++i)
+#pragma unroll
+                                for (int nt = 0; nt < 4; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], a[i], b[nt]);
+                        }
+                    } else {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         double b[4];
@@ -263,6 +283,7 @@ chol_solve_kernel(const __grid_constant__ CUtensorMap smap, const SolveParams p)
                                 for (int nt = 0; nt < 4; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], a, b[nt]);
                             }
                         }
+                    }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[stage]);   // this warp is done with the stage
